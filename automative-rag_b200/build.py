@@ -1,0 +1,87 @@
+"""Build librag_b200.so (the C-ABI library of include/rag_b200.h) with nvcc for sm_100a.
+
+Explicit `nvcc -shared` so the artefact is in-tree (automative-rag_b200/lib/librag_b200.so):
+the built .so travels to the GPU box with the repo snapshot; a JIT cache would not.
+nvcc cross-compiles without a GPU.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(HERE, "build")
+LIB = os.path.join(LIBDIR, "librag_b200.so")
+SOURCES = ["rs_api.cu", "dense_scan.cu", "topk_merge.cu", "maxsim_mma.cu", "maxsim_tc5.cu", "dense_tc5.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
+]
+
+
+def _nvcc() -> str:
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found; cannot build librag_b200.so")
+    return nvcc
+
+
+def _deps_hash(src: str) -> str:
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS).encode())
+    for name in sorted(os.listdir(CSRC)):
+        if name.endswith((".cuh", ".h")) or name == src:
+            with open(os.path.join(CSRC, name), "rb") as f:
+                h.update(f.read())
+    with open(os.path.join(HERE, "..", "include", "rag_b200.h"), "rb") as f:
+        h.update(f.read())
+    return h.hexdigest()
+
+
+def _compile(src: str, verbose: bool) -> str:
+    obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+    stamp = obj + ".hash"
+    want = _deps_hash(src)
+    if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == want:
+        return obj
+    cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    log = os.path.join(OBJDIR, src + ".ptxas.log")
+    with open(log, "w") as f:
+        f.write(proc.stdout + proc.stderr)
+    if proc.returncode != 0:
+        raise RuntimeError(f"nvcc failed on {src}:\n{proc.stdout}\n{proc.stderr}")
+    if verbose:
+        print(f"[build] compiled {src}")
+    with open(stamp, "w") as f:
+        f.write(want)
+    return obj
+
+
+def build(verbose: bool = True, force: bool = False) -> str:
+    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+    if force:
+        for f in os.listdir(OBJDIR):
+            os.remove(os.path.join(OBJDIR, f))
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        objs = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
+    newest = max(os.path.getmtime(o) for o in objs)
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
+        cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-lcudart"]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError(f"link failed:\n{proc.stdout}\n{proc.stderr}")
+        if verbose:
+            print(f"[build] linked {LIB}")
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv)

@@ -1,0 +1,61 @@
+// kernels.h — host-visible launchers of the sm_100a kernels (internal to the library).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rs {
+
+// ------------------------------------------------------------------ dense single-query scan
+struct ScanParams {
+  const void* corpus;      // [n, d] fp16 | bf16
+  const void* query;       // [d] same dtype
+  const float* inv_norm;   // [n] or null
+  const uint32_t* mask;    // bit-packed or null
+  int64_t n;
+  int32_t d;
+  int32_t k;
+  int32_t metric;          // 0 ip, 1 cosine
+  int64_t id_base;
+  uint64_t* ws_keys;       // [grid, k]
+  unsigned* ticket;        // zero-initialised once, self-resetting
+  float* out_scores;       // [k]
+  int64_t* out_ids;        // [k]
+  int32_t tile_rows;       // filled by the launcher
+  int32_t buf_cap;         // filled by the launcher
+};
+int scan_tile_rows(int d);
+size_t scan_smem_bytes(int d, int k);
+cudaError_t launch_dense_scan(ScanParams p, int dtype, int num_sms, cudaStream_t stream);
+
+// ------------------------------------------------------------------ top-k list merge
+cudaError_t launch_topk_merge(const float* scores, const int64_t* ids, int nlists, int nq, int k_in, int k_out,
+                              int64_t score_list_stride, int64_t id_list_stride, float* out_scores, int64_t* out_ids,
+                              cudaStream_t stream);
+
+// ------------------------------------------------------------------ MaxSim
+struct MaxSimParams {
+  const void* q;               // [nq, lq, d]
+  const float* q_weight;       // [nq, lq] or null (reference rule)
+  const void* doc_tokens;      // [T, d]
+  const int32_t* doc_offsets;  // [nd + 1]
+  const int32_t* cand;         // null or [nq, nc]
+  float* out_scores;           // [nq, ndo]   ndo = cand ? nc : nd
+  int32_t* out_argmax;         // null or [nq, ndo, lq]
+  int64_t n_tokens;            // rows in doc_tokens
+  int32_t nq, lq, d, nd, nc;
+};
+// warp-level mma.sync path: any lq <= 128, d % 16 == 0, ragged docs, candidate lists, argmax
+cudaError_t launch_maxsim_mma(const MaxSimParams& p, int dtype, int num_sms, cudaStream_t stream);
+size_t maxsim_mma_smem_bytes(int lq, int d);
+// exact fp32 CUDA-core path (dtype RS_F32)
+cudaError_t launch_maxsim_simt(const MaxSimParams& p, cudaStream_t stream);
+size_t maxsim_simt_smem_bytes(int lq, int d);
+
+// ------------------------------------------------------------------ rerank tail, filter mask
+cudaError_t launch_rerank_postprocess(const float* scores, const float* other, int nq, int n, float w_a, float w_b,
+                                      int top_k, int32_t* out_idx, float* out_scores, cudaStream_t stream);
+cudaError_t launch_filter_mask(const int32_t* const* cols_dev, int nclauses, const int32_t* values_dev,
+                               const int32_t* val_offsets_dev, const uint32_t* tombstone, int64_t n,
+                               uint32_t* out_mask, int num_sms, cudaStream_t stream);
+
+}  // namespace rs

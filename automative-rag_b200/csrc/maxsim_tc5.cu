@@ -1,0 +1,407 @@
+// maxsim_tc5.cu — shared-candidate ColBERT MaxSim on tcgen05 tensor cores with TMEM
+// accumulators: the batched shape of ColBERTReranker.batch_rerank_queries
+// (reference src/core/query/llm/rerankers.py:583-593 — documents encoded once, every query
+// scored against the same list with _compute_maxsim_scores :215-265).
+//
+// The stage is one contraction S = Q_all [nq*lq, d] . D_all^T [d, n_tokens] followed by a
+// segmented max over each document's tokens and a weighted sum over each query's tokens.
+// Mapping onto the hardware:
+//   * M (TMEM lanes) = query tokens, 128 per tile; N (TMEM columns) = document tokens, 256 per
+//     tile; K = d (64 or 128) fits one shared-memory stage, so there is no K pipeline.
+//     tcgen05.ld 32x32b hands thread t of an epilogue warp ONE query-token row with 32
+//     consecutive document tokens in registers, so the max over document tokens is a
+//     register-only FMNMX3 chain and the sum over a query's 32 tokens is one warp shuffle
+//     reduction.  The token-score matrix S exists only in TMEM.
+//   * each CTA keeps MG = 2 query tiles resident in shared memory (loaded once by TMA) and
+//     streams document-token tiles through a 2-stage TMA ring; every B tile feeds 2 MMAs.
+//     TMEM holds one 128x256 fp32 accumulator per resident query tile (2 x 256 = 512 columns);
+//     epilogue warp set s drains accumulator s while the tensor core fills the other one.
+//   * warp roles: 0 = TMA producer, 1 = MMA issuer (one elected thread), 2 = TMEM allocator,
+//     4..7 = epilogue set 0, 8..11 = epilogue set 1 (warp % 4 selects the TMEM lane quarter).
+//   * the grid is (document ranges) x (query-tile groups) sized to one wave of the SMs; a CTA's
+//     tiles start at its first document's first token, so document boundaries are the only
+//     segmentation the epilogue has to track (prefetched two documents ahead).
+#include <cuda.h>
+#include <math_constants.h>
+
+#include <mutex>
+
+#include "tc5.cuh"
+#include "tc5_host.h"
+
+namespace rs {
+
+constexpr int kTcThreads = 384;
+constexpr int kTcBN = 256;      // document tokens per tile (UMMA N)
+constexpr int kTcMG = 2;        // resident query tiles per CTA == TMEM accumulator slots
+constexpr int kTcStages = 2;    // B ring depth
+constexpr int kTcTmemCols = 512;
+
+struct MaxSimTcParams {
+  const float* q_weight;
+  const int32_t* doc_offsets;
+  float* out;
+  int32_t nq, lq, lq_pad, nd;
+  int32_t num_m_tiles, num_ranges;
+  int32_t accumulate;  // lq_pad > 32: several warps contribute to one (query, doc) -> atomicAdd
+};
+
+__device__ __forceinline__ float tc_reference_weight(int i, int lq) {
+  return (lq > 2 && (i == 0 || i == lq - 1)) ? 0.f : 1.f;  // rerankers.py:255-261
+}
+
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+template <bool BF16, int KH>
+__global__ void __launch_bounds__(kTcThreads, 1)
+    maxsim_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_d,
+                      const MaxSimTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t kABytesKH = 128 * 128;    // one K-half (64 elements) of a 128-row query tile
+  constexpr uint32_t kBBytesKH = kTcBN * 128;  // one K-half of a 256-token tile
+  constexpr uint32_t kABytes = kABytesKH * KH;
+  constexpr uint32_t kBBytes = kBBytesKH * KH;
+
+  // ---- work of this CTA
+  const int range = blockIdx.x, mgroup = blockIdx.y;
+  const int d0 = (int)(((int64_t)p.nd * range) / p.num_ranges);
+  const int d1 = (int)(((int64_t)p.nd * (range + 1)) / p.num_ranges);
+  if (d0 >= d1) return;  // uniform: nothing allocated yet
+  const int n_act = min(kTcMG, p.num_m_tiles - mgroup * kTcMG);
+  const int tok0 = __ldg(p.doc_offsets + d0);
+  const int tok1 = __ldg(p.doc_offsets + d1);
+  const int ntiles = (tok1 - tok0 + kTcBN - 1) / kTcBN;
+
+  // ---- shared memory carve-up (1024-byte aligned: SWIZZLE_128B atoms)
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* smA = sm;                                 // [kTcMG][KH][128 rows x 128 B]
+  uint8_t* smB = smA + kTcMG * kABytes;              // [kTcStages][KH][256 rows x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + kTcStages * kBBytes);
+  uint64_t* a_full = bars;                 // 1
+  uint64_t* b_full = bars + 1;             // kTcStages
+  uint64_t* b_empty = b_full + kTcStages;  // kTcStages
+  uint64_t* acc_full = b_empty + kTcStages;  // kTcMG
+  uint64_t* acc_empty = acc_full + kTcMG;    // kTcMG
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + kTcMG);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    mbar_init(a_full, 1);
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int a = 0; a < kTcMG; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);  // the 4 warps of an epilogue set
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, kTcTmemCols);
+    tmem_relinquish();
+  }
+  tc5_fence_before();
+  __syncthreads();
+  tc5_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr);
+
+  const int qpt = 128 / p.lq_pad;  // queries per 128-row tile
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&map_q);
+      tma_prefetch_desc(&map_d);
+      const uint64_t pol = policy_evict_normal();
+      mbar_arrive_expect_tx(a_full, (uint32_t)n_act * kABytes);
+      for (int a = 0; a < n_act; ++a)
+        for (int kh = 0; kh < KH; ++kh)
+          tma_load_3d(smA + a * kABytes + kh * kABytesKH, &map_q, kh * 64, 0, (mgroup * kTcMG + a) * qpt, a_full, pol);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j % kTcStages;
+        const uint32_t ph = (uint32_t)(j / kTcStages) & 1u;
+        mbar_wait(&b_empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&b_full[s], kBBytes);
+        for (int kh = 0; kh < KH; ++kh)
+          tma_load_2d(smB + s * kBBytes + kh * kBBytesKH, &map_d, kh * 64, tok0 + j * kTcBN, &b_full[s], pol);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BF16, 128, kTcBN);
+      mbar_wait(a_full, 0);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j % kTcStages;
+        const uint32_t ph = (uint32_t)(j / kTcStages) & 1u;
+        mbar_wait(&b_full[s], ph);
+        tc5_fence_after();
+        for (int a = 0; a < n_act; ++a) {
+          mbar_wait(&acc_empty[a], ((uint32_t)j & 1u) ^ 1u);
+          tc5_fence_after();
+#pragma unroll
+          for (int kh = 0; kh < KH; ++kh) {
+            const uint64_t da = umma_smem_desc_sw128(smem_u32(smA + a * kABytes + kh * kABytesKH));
+            const uint64_t db = umma_smem_desc_sw128(smem_u32(smB + s * kBBytes + kh * kBBytesKH));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)  // 4 x UMMA_K(16 elements = 32 B) per 128-byte swizzle row
+              umma_f16_ss(tmem_base + (uint32_t)a * kTcBN, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
+                          (kh | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(&acc_full[a]);  // accumulator a ready for its epilogue set
+        }
+        umma_commit(&b_empty[s]);  // B stage reusable once both MMAs have read it
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue sets
+    const int set = (warp - 4) >> 2;
+    const int quarter = warp & 3;  // TMEM lanes 32*quarter .. +31
+    if (set < n_act) {
+      const int mt = mgroup * kTcMG + set;
+      const int row = quarter * 32 + lane;           // row in the 128-row tile
+      const int query = mt * qpt + row / p.lq_pad;   // uniform across the warp (lq_pad % 32 == 0)
+      const int tok = row % p.lq_pad;
+      const bool q_valid = query < p.nq;
+      float w = 0.f;
+      if (q_valid && tok < p.lq)
+        w = p.q_weight ? __ldg(p.q_weight + (size_t)query * p.lq + tok) : tc_reference_weight(tok, p.lq);
+      const int32_t* off = p.doc_offsets;
+      int doc = d0;
+      int e0 = __ldg(off + d0 + 1) - tok0;
+      int e1 = (d0 + 2 <= d1) ? __ldg(off + d0 + 2) - tok0 : INT_MAX;
+      int e2 = (d0 + 3 <= d1) ? __ldg(off + d0 + 3) - tok0 : INT_MAX;
+      float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
+      float* out_row = p.out + (size_t)query * p.nd;
+
+      auto finalize = [&]() {
+        const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        const float part = warp_sum(w != 0.f ? w * m : 0.f);
+        if (lane == 0 && q_valid) {
+          if (p.accumulate)
+            atomicAdd(out_row + doc, part);
+          else
+            out_row[doc] = part;
+        }
+        m0 = m1 = m2 = m3 = -CUDART_INF_F;
+        ++doc;
+        e0 = e1;
+        e1 = e2;
+        e2 = (doc + 3 <= d1) ? __ldg(off + doc + 3) - tok0 : INT_MAX;
+        if (doc >= d1) e0 = INT_MAX;
+      };
+      auto consume = [&](const uint32_t (&v)[32], int c0) {
+        if (e0 > c0 + 32) {
+          // no document ends inside this chunk: 16 three-input max ops in 4 independent chains
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            m0 = fmaxf(fmaxf(m0, __uint_as_float(v[c + 0])), __uint_as_float(v[c + 1]));
+            m1 = fmaxf(fmaxf(m1, __uint_as_float(v[c + 2])), __uint_as_float(v[c + 3]));
+            m2 = fmaxf(fmaxf(m2, __uint_as_float(v[c + 4])), __uint_as_float(v[c + 5]));
+            m3 = fmaxf(fmaxf(m3, __uint_as_float(v[c + 6])), __uint_as_float(v[c + 7]));
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            m0 = fmaxf(m0, __uint_as_float(v[c]));
+            if (c0 + c + 1 == e0) finalize();  // warp-uniform
+          }
+        }
+      };
+
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)set * kTcBN;
+      uint32_t va[32], vb[32];
+      for (int j = 0; j < ntiles; ++j) {
+        mbar_wait(&acc_full[set], (uint32_t)j & 1u);
+        tc5_fence_after();
+        const int cbase = j * kTcBN;
+        tmem_ld_32x32(taddr, va);
+        tmem_ld_wait(va);
+#pragma unroll
+        for (int ch = 0; ch < kTcBN / 32; ch += 2) {
+          tmem_ld_32x32(taddr + (ch + 1) * 32, vb);  // in flight while chunk ch is reduced
+          consume(va, cbase + ch * 32);
+          tmem_ld_wait(vb);
+          if (ch + 2 < kTcBN / 32) {
+            tmem_ld_32x32(taddr + (ch + 2) * 32, va);
+          } else {
+            // all of this accumulator is in registers: hand the TMEM slot back to the MMA warp
+            tc5_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[set]);
+          }
+          consume(vb, cbase + (ch + 1) * 32);
+          if (ch + 2 < kTcBN / 32) tmem_ld_wait(va);
+        }
+      }
+    }
+  }
+
+  tc5_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc5_fence_after();
+    tmem_dealloc(tmem_base, kTcTmemCols);
+  }
+}
+
+// ================================================================================ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct Tc5State {
+  int device = 0;
+  int num_sms = 0;
+  EncodeTiledFn encode = nullptr;
+  // scratch of the batched dense path (dense_tc5.cu)
+  void* dense_ws = nullptr;
+  size_t dense_ws_bytes = 0;
+};
+
+Tc5State* tc5_create(int device, int num_sms) {
+  Tc5State* s = new Tc5State();
+  s->device = device;
+  s->num_sms = num_sms;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+      qres == cudaDriverEntryPointSuccess)
+    s->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  else
+    cudaGetLastError();
+  return s;
+}
+
+void tc5_destroy(Tc5State* s) {
+  if (!s) return;
+  if (s->dense_ws) cudaFree(s->dense_ws);
+  delete s;
+}
+
+void* tc5_dense_scratch(Tc5State* s, size_t bytes) {
+  if (bytes > s->dense_ws_bytes) {
+    if (s->dense_ws) cudaFree(s->dense_ws);
+    s->dense_ws = nullptr;
+    s->dense_ws_bytes = 0;
+    if (cudaMalloc(&s->dense_ws, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    s->dense_ws_bytes = bytes;
+  }
+  return s->dense_ws;
+}
+
+bool tc5_encode(const Tc5State* s, CUtensorMap* map, int dtype, int rank, const void* base, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, std::string* err) {
+  if (!s->encode) {
+    if (err) *err = "cuTensorMapEncodeTiled entry point not available";
+    return false;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = s->encode(map, dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                         (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+    return false;
+  }
+  return true;
+}
+
+int tc5_num_sms(const Tc5State* s) { return s->num_sms; }
+
+bool tc5_maxsim_supported(const Tc5State* s, int nq, int lq, int d, int nd, const int32_t* cand,
+                          const int32_t* out_argmax) {
+  if (!s || !s->encode) return false;
+  if (cand != nullptr || out_argmax != nullptr) return false;
+  if (d != 64 && d != 128) return false;
+  if (lq < 1 || lq > 128 || nd < 1) return false;
+  const int lq_pad = lq <= 32 ? 32 : (lq <= 64 ? 64 : 128);
+  return (long long)nq * lq_pad >= 128;  // at least one full 128-row tile of query tokens
+}
+
+int tc5_maxsim(Tc5State* s, const MaxSimParams& p, int dtype, cudaStream_t stream, int* launched, std::string* err) {
+  *launched = 0;
+  const int lq_pad = p.lq <= 32 ? 32 : (p.lq <= 64 ? 64 : 128);
+  const int qpt = 128 / lq_pad;
+  const int num_m_tiles = (p.nq + qpt - 1) / qpt;
+  const int mgroups = (num_m_tiles + kTcMG - 1) / kTcMG;
+  int ranges = s->num_sms / mgroups;
+  if (ranges < 1) ranges = 1;
+  if (ranges > p.nd) ranges = p.nd;
+
+  CUtensorMap map_q, map_d;
+  {
+    const uint64_t dims[3] = {(uint64_t)p.d, (uint64_t)p.lq, (uint64_t)p.nq};
+    const uint64_t strides[2] = {(uint64_t)p.d * 2, (uint64_t)p.lq * p.d * 2};
+    const uint32_t box[3] = {64, (uint32_t)lq_pad, (uint32_t)qpt};
+    if (!tc5_encode(s, &map_q, dtype, 3, p.q, dims, strides, box, err)) return -2;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)p.d, (uint64_t)p.n_tokens};
+    const uint64_t strides[1] = {(uint64_t)p.d * 2};
+    const uint32_t box[2] = {64, (uint32_t)kTcBN};
+    if (!tc5_encode(s, &map_d, dtype, 2, p.doc_tokens, dims, strides, box, err)) return -2;
+  }
+  MaxSimTcParams kp{};
+  kp.q_weight = p.q_weight;
+  kp.doc_offsets = p.doc_offsets;
+  kp.out = p.out_scores;
+  kp.nq = p.nq;
+  kp.lq = p.lq;
+  kp.lq_pad = lq_pad;
+  kp.nd = p.nd;
+  kp.num_m_tiles = num_m_tiles;
+  kp.num_ranges = ranges;
+  kp.accumulate = lq_pad > 32 ? 1 : 0;
+  if (kp.accumulate) {
+    cudaError_t e = cudaMemsetAsync(p.out_scores, 0, (size_t)p.nq * p.nd * sizeof(float), stream);
+    if (e != cudaSuccess) {
+      *err = cudaGetErrorString(e);
+      return -3;
+    }
+  }
+  const int kh = p.d / 64;
+  const size_t smem = 1024 + (size_t)kTcMG * 128 * 128 * kh + (size_t)kTcStages * kTcBN * 128 * kh + 256;
+  dim3 grid(ranges, mgroups);
+  cudaError_t e = cudaSuccess;
+#define RS_TC_LAUNCH(BF, KHV)                                                                                         \
+  {                                                                                                                   \
+    e = cudaFuncSetAttribute(maxsim_tc5_kernel<BF, KHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+    if (e == cudaSuccess) {                                                                                           \
+      maxsim_tc5_kernel<BF, KHV><<<grid, kTcThreads, smem, stream>>>(map_q, map_d, kp);                              \
+      e = cudaGetLastError();                                                                                         \
+    }                                                                                                                 \
+  }
+  if (dtype == 1) {
+    if (kh == 1) RS_TC_LAUNCH(true, 1) else RS_TC_LAUNCH(true, 2)
+  } else {
+    if (kh == 1) RS_TC_LAUNCH(false, 1) else RS_TC_LAUNCH(false, 2)
+  }
+#undef RS_TC_LAUNCH
+  if (e != cudaSuccess) {
+    *err = cudaGetErrorString(e);
+    return -3;
+  }
+  *launched = 1;
+  return 0;
+}
+
+}  // namespace rs

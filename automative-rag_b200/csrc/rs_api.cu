@@ -1,0 +1,399 @@
+// rs_api.cu — the C ABI declared in include/rag_b200.h: argument validation, kernel-family
+// choice, workspace ownership and status/last-error plumbing.  No exceptions cross the ABI.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rag_b200.h"
+#include "kernels.h"
+#include "tc5_host.h"
+
+namespace {
+thread_local std::string g_create_error;
+}
+
+struct rs_handle {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;  // internal stream of the *_host entry points
+  // dense scan workspace
+  uint64_t* ws_keys = nullptr;  // [num_sms, 2048]
+  unsigned* ticket = nullptr;
+  // *_host staging
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  void* dev_stage = nullptr;
+  size_t dev_stage_bytes = 0;
+  // small device scratch for rs_filter_mask (values, offsets)
+  int32_t* filt_dev = nullptr;
+  size_t filt_dev_ints = 0;
+  // tcgen05 paths (tensor-map cache, scratch)
+  rs::Tc5State* tc5 = nullptr;
+  int dense_impl = RS_DENSE_AUTO, maxsim_impl = RS_MAXSIM_AUTO;
+  int last_dense_impl = 0, last_maxsim_impl = 0;
+  int64_t launches = 0;
+  std::string err;
+};
+
+namespace {
+
+constexpr int kMaxK = 2048;
+
+int fail(rs_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h)
+    h->err = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+int cuda_fail(rs_handle* h, cudaError_t e, const char* what) {
+  return fail(h, RS_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int ensure_staging(rs_handle* h, size_t host_bytes, size_t dev_bytes) {
+  if (host_bytes > h->pinned_bytes) {
+    if (h->pinned) cudaFreeHost(h->pinned);
+    h->pinned = nullptr;
+    h->pinned_bytes = 0;
+    size_t want = host_bytes < (1u << 20) ? (1u << 20) : host_bytes;
+    cudaError_t e = cudaMallocHost(&h->pinned, want);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaMallocHost(staging)");
+    h->pinned_bytes = want;
+  }
+  if (dev_bytes > h->dev_stage_bytes) {
+    if (h->dev_stage) cudaFree(h->dev_stage);
+    h->dev_stage = nullptr;
+    h->dev_stage_bytes = 0;
+    size_t want = dev_bytes < (1u << 20) ? (1u << 20) : dev_bytes;
+    cudaError_t e = cudaMalloc(&h->dev_stage, want);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaMalloc(staging)");
+    h->dev_stage_bytes = want;
+  }
+  return RS_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+extern "C" {
+
+int rs_abi_version(void) { return RS_ABI_VERSION; }
+
+int rs_create(int device, rs_handle** out) {
+  if (!out) return fail(nullptr, RS_ERR_INVALID_ARG, "rs_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    return fail(nullptr, RS_ERR_NO_DEVICE,
+                "rs_create: no CUDA device visible (%s); this engine has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  }
+  if (device < 0 || device >= count) return fail(nullptr, RS_ERR_INVALID_ARG, "rs_create: device %d out of range", device);
+  cudaDeviceProp prop{};
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+  if (prop.major != 10)
+    return fail(nullptr, RS_ERR_NO_DEVICE,
+                "rs_create: device %d is sm_%d%d; the kernels are built for sm_100a only and there is no fallback",
+                device, prop.major, prop.minor);
+  DeviceGuard guard(device);
+  rs_handle* h = new (std::nothrow) rs_handle();
+  if (!h) return fail(nullptr, RS_ERR_NOMEM, "rs_create: out of host memory");
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&h->ws_keys, (size_t)h->num_sms * kMaxK * sizeof(uint64_t));
+  if (e == cudaSuccess) e = cudaMalloc(&h->ticket, 256);
+  if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, 256);
+  if (e != cudaSuccess) {
+    int rc = cuda_fail(nullptr, e, "rs_create: workspace allocation");
+    rs_destroy(h);
+    return rc;
+  }
+  h->tc5 = rs::tc5_create(device, h->num_sms);
+  *out = h;
+  return RS_OK;
+}
+
+int rs_destroy(rs_handle* h) {
+  if (!h) return RS_OK;
+  DeviceGuard guard(h->device);
+  cudaDeviceSynchronize();
+  if (h->tc5) rs::tc5_destroy(h->tc5);
+  if (h->ws_keys) cudaFree(h->ws_keys);
+  if (h->ticket) cudaFree(h->ticket);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->dev_stage) cudaFree(h->dev_stage);
+  if (h->filt_dev) cudaFree(h->filt_dev);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return RS_OK;
+}
+
+const char* rs_last_error(const rs_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+int64_t rs_launch_count(const rs_handle* h) { return h ? h->launches : 0; }
+
+int rs_set_dense_impl(rs_handle* h, int impl) {
+  if (!h || impl < RS_DENSE_AUTO || impl > RS_DENSE_TCGEN05) return fail(h, RS_ERR_INVALID_ARG, "rs_set_dense_impl: bad argument");
+  h->dense_impl = impl;
+  return RS_OK;
+}
+int rs_set_maxsim_impl(rs_handle* h, int impl) {
+  if (!h || impl < RS_MAXSIM_AUTO || impl > RS_MAXSIM_SIMT) return fail(h, RS_ERR_INVALID_ARG, "rs_set_maxsim_impl: bad argument");
+  h->maxsim_impl = impl;
+  return RS_OK;
+}
+int rs_last_dense_impl(const rs_handle* h) { return h ? h->last_dense_impl : 0; }
+int rs_last_maxsim_impl(const rs_handle* h) { return h ? h->last_maxsim_impl : 0; }
+
+// ------------------------------------------------------------------------------ dense
+int rs_dense_topk(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_t dtype, const float* inv_norm,
+                  int32_t metric, const void* queries, int32_t nq, const uint32_t* mask, int64_t mask_stride_words,
+                  int32_t k, int64_t id_base, float* out_scores, int64_t* out_ids, void* stream) {
+  if (!h) return RS_ERR_INVALID_ARG;
+  if (n < 0 || nq < 0) return fail(h, RS_ERR_INVALID_ARG, "rs_dense_topk: negative size (n=%lld nq=%d)", (long long)n, nq);
+  if (nq == 0) return RS_OK;
+  if (!queries || !out_scores || !out_ids) return fail(h, RS_ERR_INVALID_ARG, "rs_dense_topk: NULL queries/outputs");
+  if (n > 0 && !corpus) return fail(h, RS_ERR_INVALID_ARG, "rs_dense_topk: NULL corpus");
+  if (dtype != RS_F16 && dtype != RS_BF16)
+    return fail(h, RS_ERR_UNSUPPORTED, "rs_dense_topk: corpus dtype must be RS_F16 or RS_BF16 (got %d)", dtype);
+  if (metric != RS_METRIC_IP && metric != RS_METRIC_COSINE) return fail(h, RS_ERR_INVALID_ARG, "rs_dense_topk: bad metric %d", metric);
+  if (d <= 0 || (d % 8) != 0 || d > 4096)
+    return fail(h, RS_ERR_UNSUPPORTED, "rs_dense_topk: d must be a multiple of 8 in [8, 4096] (got %d)", d);
+  if (k < 1 || k > kMaxK) return fail(h, RS_ERR_UNSUPPORTED, "rs_dense_topk: k must be in [1, %d] (got %d)", kMaxK, k);
+  if (n >= (1ll << 32)) return fail(h, RS_ERR_UNSUPPORTED, "rs_dense_topk: n must be < 2^32 rows per shard");
+  if (!aligned16(corpus) || !aligned16(queries))
+    return fail(h, RS_ERR_INVALID_ARG, "rs_dense_topk: corpus and queries must be 16-byte aligned");
+  if (mask_stride_words < 0) return fail(h, RS_ERR_INVALID_ARG, "rs_dense_topk: negative mask stride");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  int impl = h->dense_impl;
+  if (impl == RS_DENSE_AUTO) impl = rs::tc5_dense_supported(h->tc5, n, d, nq, k, mask, mask_stride_words) ? RS_DENSE_TCGEN05 : RS_DENSE_SCAN;
+  if (impl == RS_DENSE_TCGEN05) {
+    if (!rs::tc5_dense_supported(h->tc5, n, d, nq, k, mask, mask_stride_words))
+      return fail(h, RS_ERR_UNSUPPORTED, "rs_dense_topk: tcgen05 batched path needs nq >= 16, d %% 64 == 0, k <= 128, shared mask");
+    int launched = 0;
+    std::string err;
+    int rc = rs::tc5_dense_topk(h->tc5, corpus, n, d, dtype, inv_norm, metric, queries, nq, mask, k, id_base, out_scores,
+                                out_ids, st, &launched, &err);
+    h->launches += launched;
+    h->last_dense_impl = RS_DENSE_TCGEN05;
+    if (rc != RS_OK) return fail(h, rc, "rs_dense_topk(tcgen05): %s", err.c_str());
+    return RS_OK;
+  }
+
+  h->last_dense_impl = RS_DENSE_SCAN;
+  const size_t elt = 2;
+  for (int qi = 0; qi < nq; ++qi) {
+    rs::ScanParams p{};
+    p.corpus = corpus;
+    p.query = static_cast<const uint8_t*>(queries) + (size_t)qi * d * elt;
+    p.inv_norm = (metric == RS_METRIC_COSINE) ? inv_norm : nullptr;
+    p.mask = mask ? mask + (size_t)qi * mask_stride_words : nullptr;
+    p.n = n;
+    p.d = d;
+    p.k = k;
+    p.metric = metric;
+    p.id_base = id_base;
+    p.ws_keys = h->ws_keys;
+    p.ticket = h->ticket;
+    p.out_scores = out_scores + (size_t)qi * k;
+    p.out_ids = out_ids + (size_t)qi * k;
+    cudaError_t e = rs::launch_dense_scan(p, dtype, h->num_sms, st);
+    if (e != cudaSuccess) return cuda_fail(h, e, "dense_scan_kernel launch");
+    h->launches += 1;
+  }
+  return RS_OK;
+}
+
+int rs_dense_topk_host(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_t dtype, const float* inv_norm,
+                       int32_t metric, const void* queries_host, int32_t nq, const uint32_t* mask_host,
+                       const uint32_t* mask_dev, int64_t mask_stride_words, int32_t k, int64_t id_base,
+                       float* out_scores_host, int64_t* out_ids_host) {
+  if (!h) return RS_ERR_INVALID_ARG;
+  if (nq < 0 || n < 0) return fail(h, RS_ERR_INVALID_ARG, "rs_dense_topk_host: negative size");
+  if (nq == 0) return RS_OK;
+  if (!queries_host || !out_scores_host || !out_ids_host) return fail(h, RS_ERR_INVALID_ARG, "rs_dense_topk_host: NULL host buffer");
+  if (d <= 0 || k < 1 || k > kMaxK) return fail(h, RS_ERR_INVALID_ARG, "rs_dense_topk_host: bad d/k");
+  DeviceGuard guard(h->device);
+  const size_t q_bytes = align_up((size_t)nq * d * 2, 256);
+  const size_t words_per_mask = (size_t)((n + 31) / 32);
+  const size_t n_masks = mask_host ? (mask_stride_words ? (size_t)nq : 1) : 0;
+  const size_t m_bytes = align_up(mask_host ? ((n_masks - 1) * (size_t)mask_stride_words + words_per_mask) * 4 : 0, 256);
+  const size_t os_bytes = align_up((size_t)nq * k * 4, 256);
+  const size_t oi_bytes = align_up((size_t)nq * k * 8, 256);
+  const size_t total = q_bytes + m_bytes + os_bytes + oi_bytes;
+  int rc = ensure_staging(h, total, total);
+  if (rc != RS_OK) return rc;
+  uint8_t* hp = static_cast<uint8_t*>(h->pinned);
+  uint8_t* dp = static_cast<uint8_t*>(h->dev_stage);
+  memcpy(hp, queries_host, (size_t)nq * d * 2);
+  if (mask_host) memcpy(hp + q_bytes, mask_host, ((n_masks - 1) * (size_t)mask_stride_words + words_per_mask) * 4);
+  cudaError_t e = cudaMemcpyAsync(dp, hp, q_bytes + m_bytes, cudaMemcpyHostToDevice, h->stream);
+  if (e != cudaSuccess) return cuda_fail(h, e, "H2D(queries, mask)");
+  const uint32_t* mask = mask_host ? reinterpret_cast<const uint32_t*>(dp + q_bytes) : mask_dev;
+  float* d_scores = reinterpret_cast<float*>(dp + q_bytes + m_bytes);
+  int64_t* d_ids = reinterpret_cast<int64_t*>(dp + q_bytes + m_bytes + os_bytes);
+  rc = rs_dense_topk(h, corpus, n, d, dtype, inv_norm, metric, dp, nq, mask, mask_stride_words, k, id_base, d_scores,
+                     d_ids, h->stream);
+  if (rc != RS_OK) return rc;
+  e = cudaMemcpyAsync(hp + q_bytes + m_bytes, dp + q_bytes + m_bytes, os_bytes + oi_bytes, cudaMemcpyDeviceToHost, h->stream);
+  if (e != cudaSuccess) return cuda_fail(h, e, "D2H(results)");
+  e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) return cuda_fail(h, e, "rs_dense_topk_host: stream synchronize");
+  memcpy(out_scores_host, hp + q_bytes + m_bytes, (size_t)nq * k * 4);
+  memcpy(out_ids_host, hp + q_bytes + m_bytes + os_bytes, (size_t)nq * k * 8);
+  return RS_OK;
+}
+
+int rs_topk_merge(rs_handle* h, const float* scores, const int64_t* ids, int32_t nlists, int32_t nq, int32_t k_in,
+                  int32_t k_out, int64_t score_list_stride, int64_t id_list_stride, float* out_scores, int64_t* out_ids,
+                  void* stream) {
+  if (!h) return RS_ERR_INVALID_ARG;
+  if (nq == 0) return RS_OK;
+  if (!scores || !ids || !out_scores || !out_ids) return fail(h, RS_ERR_INVALID_ARG, "rs_topk_merge: NULL buffer");
+  if (nlists < 1 || nq < 0 || k_in < 1 || k_out < 1 || score_list_stride < 0 || id_list_stride < 0)
+    return fail(h, RS_ERR_INVALID_ARG, "rs_topk_merge: bad sizes");
+  if ((long long)nlists * k_in > 16384 || k_out > 16384)
+    return fail(h, RS_ERR_UNSUPPORTED, "rs_topk_merge: nlists * k_in must be <= 16384 (got %lld)", (long long)nlists * k_in);
+  DeviceGuard guard(h->device);
+  cudaError_t e = rs::launch_topk_merge(scores, ids, nlists, nq, k_in, k_out, score_list_stride, id_list_stride, out_scores,
+                                        out_ids, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(h, e, "topk_merge_kernel launch");
+  h->launches += 1;
+  return RS_OK;
+}
+
+// ------------------------------------------------------------------------------ MaxSim
+int rs_maxsim(rs_handle* h, const void* q, int32_t nq, int32_t lq, int32_t d, int32_t dtype, const float* q_weight,
+              const void* doc_tokens, int64_t n_tokens, const int32_t* doc_offsets, int32_t nd, const int32_t* cand,
+              int32_t nc, float* out_scores, int32_t* out_argmax, void* stream) {
+  if (!h) return RS_ERR_INVALID_ARG;
+  if (nq < 0 || nd < 0 || nc < 0) return fail(h, RS_ERR_INVALID_ARG, "rs_maxsim: negative size");
+  const int ndo = cand ? nc : nd;
+  if (nq == 0 || ndo == 0) return RS_OK;  // empty documents -> [] (rerankers.py:281-282,364-365)
+  if (!q || !doc_tokens || !doc_offsets || !out_scores) return fail(h, RS_ERR_INVALID_ARG, "rs_maxsim: NULL buffer");
+  if (lq < 1 || d < 1) return fail(h, RS_ERR_INVALID_ARG, "rs_maxsim: lq and d must be positive");
+  if (n_tokens < 1 || n_tokens >= (1ll << 31)) return fail(h, RS_ERR_INVALID_ARG, "rs_maxsim: n_tokens must be in [1, 2^31)");
+  if (dtype != RS_F16 && dtype != RS_BF16 && dtype != RS_F32) return fail(h, RS_ERR_UNSUPPORTED, "rs_maxsim: bad dtype %d", dtype);
+  DeviceGuard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rs::MaxSimParams p{q, q_weight, doc_tokens, doc_offsets, cand, out_scores, out_argmax, n_tokens, nq, lq, d, nd, nc};
+
+  if (dtype == RS_F32) {
+    if (h->maxsim_impl != RS_MAXSIM_AUTO && h->maxsim_impl != RS_MAXSIM_SIMT)
+      return fail(h, RS_ERR_UNSUPPORTED, "rs_maxsim: fp32 inputs run only on the SIMT path");
+    if (rs::maxsim_simt_smem_bytes(lq, d) > 200 * 1024)
+      return fail(h, RS_ERR_UNSUPPORTED, "rs_maxsim(fp32): lq * d too large for shared memory (lq=%d d=%d)", lq, d);
+    cudaError_t e = rs::launch_maxsim_simt(p, st);
+    if (e != cudaSuccess) return cuda_fail(h, e, "maxsim_simt_kernel launch");
+    h->launches += 1;
+    h->last_maxsim_impl = RS_MAXSIM_SIMT;
+    return RS_OK;
+  }
+  if (h->maxsim_impl == RS_MAXSIM_SIMT) return fail(h, RS_ERR_UNSUPPORTED, "rs_maxsim: SIMT path takes fp32 inputs only");
+  if (!aligned16(q) || !aligned16(doc_tokens)) return fail(h, RS_ERR_INVALID_ARG, "rs_maxsim: q and doc_tokens must be 16-byte aligned");
+
+  int impl = h->maxsim_impl;
+  const bool tc5_ok = rs::tc5_maxsim_supported(h->tc5, nq, lq, d, nd, cand, out_argmax);
+  if (impl == RS_MAXSIM_AUTO) impl = tc5_ok ? RS_MAXSIM_TCGEN05 : RS_MAXSIM_MMA;
+  if (impl == RS_MAXSIM_TCGEN05) {
+    if (!tc5_ok)
+      return fail(h, RS_ERR_UNSUPPORTED,
+                  "rs_maxsim: tcgen05 path needs shared candidates, no argmax, lq <= 128, d in {64,128,192,256}");
+    int launched = 0;
+    std::string err;
+    int rc = rs::tc5_maxsim(h->tc5, p, dtype, st, &launched, &err);
+    h->launches += launched;
+    h->last_maxsim_impl = RS_MAXSIM_TCGEN05;
+    if (rc != RS_OK) return fail(h, rc, "rs_maxsim(tcgen05): %s", err.c_str());
+    return RS_OK;
+  }
+  if ((d % 16) != 0) return fail(h, RS_ERR_UNSUPPORTED, "rs_maxsim: d must be a multiple of 16 for fp16/bf16 (got %d)", d);
+  if (lq > 128) return fail(h, RS_ERR_UNSUPPORTED, "rs_maxsim: lq must be <= 128 (got %d)", lq);
+  if (rs::maxsim_mma_smem_bytes(lq, d) > 220 * 1024)
+    return fail(h, RS_ERR_UNSUPPORTED, "rs_maxsim: lq=%d d=%d does not fit shared memory", lq, d);
+  cudaError_t e = rs::launch_maxsim_mma(p, dtype, h->num_sms, st);
+  if (e != cudaSuccess) return cuda_fail(h, e, "maxsim_mma_kernel launch");
+  h->launches += 1;
+  h->last_maxsim_impl = RS_MAXSIM_MMA;
+  return RS_OK;
+}
+
+int rs_rerank_postprocess(rs_handle* h, const float* scores, const float* other, int32_t nq, int32_t n, float w_a,
+                          float w_b, int32_t top_k, int32_t* out_idx, float* out_scores, void* stream) {
+  if (!h) return RS_ERR_INVALID_ARG;
+  if (nq == 0 || top_k == 0) return RS_OK;
+  if (!scores || !out_idx || !out_scores) return fail(h, RS_ERR_INVALID_ARG, "rs_rerank_postprocess: NULL buffer");
+  if (nq < 0 || n < 1 || top_k < 0) return fail(h, RS_ERR_INVALID_ARG, "rs_rerank_postprocess: bad sizes");
+  if (n > 4096) return fail(h, RS_ERR_UNSUPPORTED, "rs_rerank_postprocess: n must be <= 4096 (got %d)", n);
+  DeviceGuard guard(h->device);
+  cudaError_t e = rs::launch_rerank_postprocess(scores, other, nq, n, w_a, w_b, top_k, out_idx, out_scores,
+                                                static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(h, e, "rerank_postprocess_kernel launch");
+  h->launches += 1;
+  return RS_OK;
+}
+
+int rs_filter_mask(rs_handle* h, const int32_t* const* cols, int32_t nclauses, const int32_t* values,
+                   const int32_t* val_offsets, const uint32_t* tombstone, int64_t n, uint32_t* out_mask, void* stream) {
+  if (!h) return RS_ERR_INVALID_ARG;
+  if (n < 0 || nclauses < 0) return fail(h, RS_ERR_INVALID_ARG, "rs_filter_mask: negative size");
+  if (n == 0) return RS_OK;
+  if (!out_mask) return fail(h, RS_ERR_INVALID_ARG, "rs_filter_mask: NULL out_mask");
+  if (nclauses > 16) return fail(h, RS_ERR_UNSUPPORTED, "rs_filter_mask: at most 16 clauses (got %d)", nclauses);
+  if (nclauses > 0 && (!cols || !values || !val_offsets)) return fail(h, RS_ERR_INVALID_ARG, "rs_filter_mask: NULL clause arrays");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nvals = nclauses > 0 ? val_offsets[nclauses] : 0;
+  const size_t ints = (size_t)nvals + nclauses + 1;
+  if (ints > h->filt_dev_ints) {
+    if (h->filt_dev) cudaFree(h->filt_dev);
+    h->filt_dev = nullptr;
+    h->filt_dev_ints = 0;
+    size_t want = ints < 4096 ? 4096 : ints;
+    cudaError_t e = cudaMalloc(&h->filt_dev, want * sizeof(int32_t));
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaMalloc(filter scratch)");
+    h->filt_dev_ints = want;
+  }
+  std::vector<int32_t> stage(ints);
+  for (int i = 0; i <= nclauses; ++i) stage[i] = nclauses > 0 ? val_offsets[i] : 0;
+  for (int i = 0; i < nvals; ++i) stage[nclauses + 1 + i] = values[i];
+  // pageable -> device copy: the runtime stages it before returning, so `stage` may go away
+  cudaError_t e = cudaMemcpyAsync(h->filt_dev, stage.data(), ints * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return cuda_fail(h, e, "H2D(filter clauses)");
+  e = rs::launch_filter_mask(cols, nclauses, h->filt_dev + nclauses + 1, h->filt_dev, tombstone, n, out_mask, h->num_sms, st);
+  if (e != cudaSuccess) return cuda_fail(h, e, "filter_mask_kernel launch");
+  h->launches += 1;
+  return RS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+// topk_buffer.cuh — CTA-level running top-k over a stream of u64 result keys.
+//
+// A shared-memory buffer of C = pow2 >= max(2k, 512) keys plus a threshold (the current
+// k-th best key).  Producers append only keys above the threshold; when the buffer passes its
+// high-water mark H = C/2 the CTA sorts it (bitonic, descending), keeps the best k and raises
+// the threshold.  The caller guarantees that no more than C - H keys are appended between two
+// `maybe_compact` calls (H >= k always holds), so appends never overflow.
+//
+// This replaces a per-thread heap: after the first few hundred rows almost nothing beats the
+// threshold (expected appends ~ k * ln(rows / k)), so the common path is one compare per row.
+#pragma once
+#include "common.cuh"
+
+namespace rs {
+
+struct TopKBuffer {
+  uint64_t* keys;     // [C] shared
+  uint64_t* thr;      // shared: current threshold key (0 = none yet)
+  int* cnt;           // shared: number of valid keys
+  int C, k;
+  int tid, nthreads;  // participating threads (named barrier `bar_id`)
+  int bar_id;
+
+  __device__ __forceinline__ int high_water() const { return C >> 1; }
+
+  static __host__ __device__ __forceinline__ int capacity_for(int k) {
+    int c = 512;
+    while (c < 2 * k) c <<= 1;
+    return c;
+  }
+
+  // all participating threads
+  __device__ __forceinline__ void init() {
+    for (int i = tid; i < C; i += nthreads) keys[i] = 0ull;
+    if (tid == 0) {
+      *thr = 0ull;
+      *cnt = 0;
+    }
+    named_bar_sync(bar_id, nthreads);
+  }
+
+  __device__ __forceinline__ uint64_t threshold() const { return *reinterpret_cast<volatile uint64_t*>(thr); }
+
+  // Warp-cooperative append: every lane of a fully converged warp calls this; lanes with
+  // `want` set contribute `key`.
+  __device__ __forceinline__ void warp_append(bool want, uint64_t key) {
+    unsigned m = __ballot_sync(0xFFFFFFFFu, want);
+    if (m == 0) return;
+    int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(cnt, __popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (want) {
+      int pos = base + __popc(m & ((1u << lane) - 1u));
+      if (pos < C) keys[pos] = key;  // guarded; the caller's contract makes this always true
+    }
+  }
+
+  // all participating threads; sorts, truncates to k, raises the threshold.
+  __device__ __forceinline__ void compact() {
+    named_bar_sync(bar_id, nthreads);
+    int n = min(*reinterpret_cast<volatile int*>(cnt), C);
+    // clear the tail so that stale keys never survive the sort
+    for (int i = n + tid; i < C; i += nthreads) keys[i] = 0ull;
+    bitonic_sort_desc(keys, C, tid, nthreads, bar_id);
+    if (tid == 0) {
+      int kept = min(n, k);
+      *cnt = kept;
+      *thr = (kept == k) ? keys[k - 1] : 0ull;
+    }
+    named_bar_sync(bar_id, nthreads);
+  }
+
+  // Barrier + uniform decision: compacts iff any thread saw the buffer above high water.
+  __device__ __forceinline__ void maybe_compact() {
+    bool over = *reinterpret_cast<volatile int*>(cnt) > high_water();
+    if (named_bar_or(bar_id, nthreads, over)) compact();
+  }
+};
+
+}  // namespace rs

@@ -1,0 +1,234 @@
+// topk_merge.cu — small integer/sort kernels around the two scoring stages:
+//   * topk_merge_kernel: merge per-shard top-k lists after the one all-gather
+//   * rerank_postprocess_kernel: the sort / min-max / blend / [:top_k] tail of
+//     ColBERTReranker.rerank (reference src/core/query/llm/rerankers.py:302-343,377-380)
+//   * filter_mask_kernel: _build_filter predicate (vectorstore.py:216-276) over columnar
+//     metadata -> bit-packed row mask
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rs {
+
+constexpr int kMergeThreads = 512;
+constexpr int kMergeBar = 1;
+
+// One CTA per query.  All nlists*k_in candidates are loaded into shared memory as
+// (orderable score, position) keys and bitonic-sorted; runs of equal score are then ordered by
+// ascending id so the result obeys the ABI's (score desc, id asc) total order even when shard
+// id ranges interleave.
+__global__ void __launch_bounds__(kMergeThreads) topk_merge_kernel(const float* __restrict__ scores,
+                                                                   const int64_t* __restrict__ ids, int nlists, int nq,
+                                                                   int k_in, int k_out, int cap, int64_t sstride,
+                                                                   int64_t istride,
+                                                                   float* __restrict__ out_scores,
+                                                                   int64_t* __restrict__ out_ids) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem);  // [cap]
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const int m = nlists * k_in;
+  for (int i = tid; i < cap; i += kMergeThreads) {
+    uint64_t key = 0ull;
+    if (i < m) {
+      const int list = i / k_in, j = i - list * k_in;
+      const size_t in_list = (size_t)q * k_in + j;
+      if (ids[(size_t)list * istride + in_list] >= 0) key = make_key(scores[(size_t)list * sstride + in_list], (uint32_t)i);
+    }
+    keys[i] = key;
+  }
+  bitonic_sort_desc(keys, cap, tid, kMergeThreads, kMergeBar);
+  // position in the final order: rank inside the run of equal scores is by ascending id
+  for (int i = tid; i < min(m, cap); i += kMergeThreads) {
+    const uint64_t key = keys[i];
+    if (key == 0ull) continue;
+    const uint32_t so = (uint32_t)(key >> 32);
+    const int pos = (int)key_row(key);
+    const int64_t id = ids[(size_t)(pos / k_in) * istride + (size_t)q * k_in + (pos % k_in)];
+    int lo = i;
+    while (lo > 0 && (uint32_t)(keys[lo - 1] >> 32) == so) --lo;
+    int rank = 0;
+    bool tie = (lo != i) || (i + 1 < cap && (uint32_t)(keys[i + 1] >> 32) == so && keys[i + 1] != 0ull);
+    if (tie) {
+      for (int j = lo; j < cap && keys[j] != 0ull && (uint32_t)(keys[j] >> 32) == so; ++j) {
+        const int pj = (int)key_row(keys[j]);
+        const int64_t idj = ids[(size_t)(pj / k_in) * istride + (size_t)q * k_in + (pj % k_in)];
+        if (idj < id || (idj == id && j < i)) ++rank;
+      }
+    } else {
+      lo = i;
+    }
+    const int dst = lo + rank;
+    if (dst < k_out) {
+      out_scores[(size_t)q * k_out + dst] = key_score(key);
+      out_ids[(size_t)q * k_out + dst] = id;
+    }
+  }
+  // padding
+  named_bar_sync(kMergeBar, kMergeThreads);
+  for (int i = tid; i < k_out; i += kMergeThreads) {
+    if (i >= cap || keys[i] == 0ull) {
+      out_scores[(size_t)q * k_out + i] = -CUDART_INF_F;
+      out_ids[(size_t)q * k_out + i] = -1;
+    }
+  }
+}
+
+cudaError_t launch_topk_merge(const float* scores, const int64_t* ids, int nlists, int nq, int k_in, int k_out,
+                              int64_t score_list_stride, int64_t id_list_stride, float* out_scores, int64_t* out_ids,
+                              cudaStream_t stream) {
+  if (score_list_stride == 0) score_list_stride = (int64_t)nq * k_in;
+  if (id_list_stride == 0) id_list_stride = (int64_t)nq * k_in;
+  int cap = 64;
+  while (cap < nlists * k_in) cap <<= 1;
+  const size_t smem = (size_t)cap * 8;
+  cudaError_t e = cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  topk_merge_kernel<<<nq, kMergeThreads, smem, stream>>>(scores, ids, nlists, nq, k_in, k_out, cap, score_list_stride,
+                                                         id_list_stride, out_scores, out_ids);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------- rerank tail
+// One CTA per query row.  Stable descending order == sort by key (orderable score, ~position):
+// on equal scores the earlier position comes first, exactly Python's stable
+// sorted(..., key=score, reverse=True) (rerankers.py:377-380).  With a second score vector the
+// reference first orders by the ColBERT score, then min-max normalises both vectors, blends and
+// stably re-sorts THAT order (rerankers.py:298-339) — so blended ties keep ColBERT order, which
+// is why the second pass keys on the rank from the first pass, not on the input index.
+__global__ void __launch_bounds__(kMergeThreads) rerank_postprocess_kernel(const float* __restrict__ scores,
+                                                                           const float* __restrict__ other, int n,
+                                                                           int cap, float w_a, float w_b, int top_k,
+                                                                           int32_t* __restrict__ out_idx,
+                                                                           float* __restrict__ out_scores) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem);  // [cap]
+  int* perm = reinterpret_cast<int*>(keys + cap);      // [cap] rank after pass 1 -> input index
+  float* red = reinterpret_cast<float*>(perm + cap);   // [4 * 32]
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* a = scores + (size_t)q * n;
+  const float* b = other ? other + (size_t)q * n : nullptr;
+  for (int i = tid; i < cap; i += kMergeThreads) keys[i] = (i < n) ? make_key(a[i], (uint32_t)i) : 0ull;
+  bitonic_sort_desc(keys, cap, tid, kMergeThreads, kMergeBar);
+  if (b) {
+    float amin = CUDART_INF_F, amax = -CUDART_INF_F, bmin = CUDART_INF_F, bmax = -CUDART_INF_F;
+    for (int i = tid; i < n; i += kMergeThreads) {
+      float x = a[i], y = b[i];
+      amin = fminf(amin, x);
+      amax = fmaxf(amax, x);
+      bmin = fminf(bmin, y);
+      bmax = fmaxf(bmax, y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      amin = fminf(amin, __shfl_xor_sync(0xFFFFFFFFu, amin, o));
+      amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, o));
+      bmin = fminf(bmin, __shfl_xor_sync(0xFFFFFFFFu, bmin, o));
+      bmax = fmaxf(bmax, __shfl_xor_sync(0xFFFFFFFFu, bmax, o));
+    }
+    if (lane == 0) {
+      red[warp] = amin;
+      red[32 + warp] = amax;
+      red[64 + warp] = bmin;
+      red[96 + warp] = bmax;
+    }
+    __syncthreads();
+    for (int w = 0; w < kMergeThreads / 32; ++w) {
+      amin = fminf(amin, red[w]);
+      amax = fmaxf(amax, red[32 + w]);
+      bmin = fminf(bmin, red[64 + w]);
+      bmax = fmaxf(bmax, red[96 + w]);
+    }
+    const float ar = amax - amin, br = bmax - bmin;
+    for (int r = tid; r < cap; r += kMergeThreads) {
+      const uint64_t key = keys[r];
+      uint64_t key2 = 0ull;
+      int src = -1;
+      if (key != 0ull) {
+        src = (int)key_row(key);
+        // (score - min) / range, all-equal -> 1.0 (rerankers.py:302-310, :319-327); blend :330-333
+        const float na = ar > 0.f ? (a[src] - amin) / ar : 1.f;
+        const float nb = br > 0.f ? (b[src] - bmin) / br : 1.f;
+        key2 = make_key(w_a * na + w_b * nb, (uint32_t)r);
+      }
+      perm[r] = src;
+      keys[r] = key2;  // slot r is read and written by this thread only
+    }
+    bitonic_sort_desc(keys, cap, tid, kMergeThreads, kMergeBar);
+  }
+  for (int i = tid; i < top_k; i += kMergeThreads) {
+    const uint64_t key = (i < cap) ? keys[i] : 0ull;
+    if (key == 0ull) {
+      out_idx[(size_t)q * top_k + i] = -1;
+      out_scores[(size_t)q * top_k + i] = -CUDART_INF_F;
+    } else {
+      const int r = (int)key_row(key);
+      out_idx[(size_t)q * top_k + i] = b ? perm[r] : r;
+      out_scores[(size_t)q * top_k + i] = key_score(key);
+    }
+  }
+}
+
+cudaError_t launch_rerank_postprocess(const float* scores, const float* other, int nq, int n, float w_a, float w_b,
+                                      int top_k, int32_t* out_idx, float* out_scores, cudaStream_t stream) {
+  int cap = 64;
+  while (cap < n) cap <<= 1;
+  const size_t smem = (size_t)cap * 12 + 128 * 4;
+  cudaError_t e =
+      cudaFuncSetAttribute(rerank_postprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  rerank_postprocess_kernel<<<nq, kMergeThreads, smem, stream>>>(scores, other, n, cap, w_a, w_b, top_k, out_idx,
+                                                                 out_scores);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------- filter -> bitmask
+// Thread i tests row i against every clause (AND over clauses, OR inside a clause); a warp
+// ballot packs 32 rows into one mask word, so the column reads and the mask write are both
+// fully coalesced.  Pure HBM-bound integer work: 4 bytes per row per clause in, 1 bit out.
+constexpr int kFilterMaxClauses = 16;
+struct FilterClauses {
+  const int32_t* col[kFilterMaxClauses];
+};
+
+__global__ void __launch_bounds__(256) filter_mask_kernel(FilterClauses fc, int nclauses,
+                                                          const int32_t* __restrict__ values,
+                                                          const int32_t* __restrict__ val_offsets,
+                                                          const uint32_t* __restrict__ tombstone, int64_t n,
+                                                          uint32_t* __restrict__ out_mask) {
+  const int64_t nwords = (n + 31) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < nwords;
+       w += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const int64_t row = w * 32 + lane;
+    bool pass = row < n;
+    for (int c = 0; c < nclauses && __any_sync(0xFFFFFFFFu, pass); ++c) {
+      const int v0 = __ldg(val_offsets + c), v1 = __ldg(val_offsets + c + 1);
+      bool hit = false;
+      if (pass) {
+        const int32_t x = __ldg(fc.col[c] + row);
+        for (int v = v0; v < v1; ++v) hit |= (x == __ldg(values + v));
+      }
+      pass = pass && hit;
+    }
+    uint32_t word = __ballot_sync(0xFFFFFFFFu, pass);
+    if (tombstone) word &= ~__ldg(tombstone + w);
+    if (lane == 0) out_mask[w] = word;
+  }
+}
+
+cudaError_t launch_filter_mask(const int32_t* const* cols_host, int nclauses, const int32_t* values_dev,
+                               const int32_t* val_offsets_dev, const uint32_t* tombstone, int64_t n,
+                               uint32_t* out_mask, int num_sms, cudaStream_t stream) {
+  FilterClauses fc{};
+  for (int c = 0; c < nclauses; ++c) fc.col[c] = cols_host[c];
+  const int64_t nwords = (n + 31) >> 5;
+  int64_t blocks = (nwords + 7) / 8;
+  const int64_t cap = (int64_t)num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  filter_mask_kernel<<<(int)blocks, 256, 0, stream>>>(fc, nclauses, values_dev, val_offsets_dev, tombstone, n, out_mask);
+  return cudaGetLastError();
+}
+
+}  // namespace rs

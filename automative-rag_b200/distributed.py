@@ -1,0 +1,133 @@
+"""Multi-GPU sharding of the two stages: one process per GPU, `torch.distributed`
+(NCCL over NVLink/NVSwitch) for the plumbing, ONE all-gather per stage.
+
+Dense: the corpus is row-partitioned (contiguous block per rank, global id = shard offset + local
+row; the filter mask is partitioned the same way); every rank holds every query, runs its local
+top-k, contributes k (id, score) pairs per query to a single all-gather, and merges the G lists
+with `rs_topk_merge` — so every rank ends with the identical global top-k.
+MaxSim: candidate documents are partitioned by rank; local scores, the same all-gather, then the
+rerank tail on every rank.
+
+The reference has no multi-GPU code; correctness here means identical results for G in {1,2,4,8}.
+The plumbing (shard bounds, wire format, gather) is separated from the engine calls so it can be
+exercised with the gloo backend on CPU.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous block partition of n rows: rank r owns [lo, hi); sizes differ by at most 1."""
+    base, rem = divmod(n, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def wire_words(nq: int, k: int) -> int:
+    """int32 words of one rank's contribution: nq*k int64 ids followed by nq*k fp32 scores,
+    rounded up to an even count so every rank's block stays 8-byte aligned in the gather output."""
+    return (3 * nq * k + 1) // 2 * 2
+
+
+def wire_views(buf: torch.Tensor, nq: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(scores fp32 [nq, k], ids int64 [nq, k]) views into one rank's int32 wire buffer."""
+    ids = buf[: 2 * nq * k].view(torch.int64).view(nq, k)
+    scores = buf[2 * nq * k: 3 * nq * k].view(torch.float32).view(nq, k)
+    return scores, ids
+
+
+def gathered_views(gathered: torch.Tensor, world_size: int, nq: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Views [G, nq, k] of scores and ids inside the all-gather output (int32 [G * 3*nq*k])."""
+    g = gathered.view(world_size, wire_words(nq, k))
+    ids = g[:, : 2 * nq * k].view(torch.int64).view(world_size, nq, k)
+    scores = g[:, 2 * nq * k: 3 * nq * k].view(torch.float32).view(world_size, nq, k)
+    return scores, ids
+
+
+def all_gather_topk(buf: torch.Tensor, group=None) -> torch.Tensor:
+    """The one collective of the stage: every rank's wire buffer -> [G * words] on every rank."""
+    world = dist.get_world_size(group)
+    out = torch.empty(world * buf.numel(), dtype=buf.dtype, device=buf.device)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    return out
+
+
+class ShardedDenseIndex:
+    """Row shard of a dense corpus on this rank's GPU + the all-gather merge.
+
+    `local_search(queries, k, mask, out_scores, out_ids)` and `merge(scores [G,nq,k], ids [G,nq,k], k)`
+    default to the engine (`rs_dense_topk`, `rs_topk_merge`); tests inject CPU stand-ins to run the
+    plumbing under gloo.
+    """
+
+    def __init__(self, local_corpus: torch.Tensor, id_base: int, *, engine=None, inv_norm: Optional[torch.Tensor] = None,
+                 metric: int = 1, group=None, local_search: Optional[Callable] = None, merge: Optional[Callable] = None):
+        self.corpus = local_corpus
+        self.id_base = int(id_base)
+        self.engine = engine
+        self.inv_norm = inv_norm
+        self.metric = metric
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._local_search = local_search or self._engine_search
+        self._merge = merge or self._engine_merge
+        self._wire: Optional[torch.Tensor] = None
+
+    def _engine_search(self, queries, k, mask, out_scores, out_ids):
+        self.engine.dense_topk(self.corpus, queries, k, mask=mask, inv_norm=self.inv_norm, metric=self.metric,
+                               id_base=self.id_base, out_scores=out_scores, out_ids=out_ids)
+
+    def _engine_merge(self, scores, ids, k):
+        return self.engine.topk_merge(scores, ids, k)
+
+    def search(self, queries: torch.Tensor, k: int, mask: Optional[torch.Tensor] = None
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """queries [nq, d] replicated on every rank; mask covers this rank's rows.  Returns the global
+        (scores [nq, k], ids [nq, k]), identical on every rank."""
+        if queries.dim() == 1:
+            queries = queries.unsqueeze(0)
+        nq = queries.shape[0]
+        words = wire_words(nq, k)
+        if self._wire is None or self._wire.numel() != words or self._wire.device != queries.device:
+            self._wire = torch.empty(words, dtype=torch.int32, device=queries.device)
+        scores, ids = wire_views(self._wire, nq, k)
+        self._local_search(queries, k, mask, scores, ids)
+        if self.world == 1:
+            return scores, ids
+        gathered = all_gather_topk(self._wire, self.group)
+        g_scores, g_ids = gathered_views(gathered, self.world, nq, k)
+        return self._merge(g_scores, g_ids, k)
+
+
+class ShardedMaxSim:
+    """Candidate documents partitioned by rank; queries replicated; one all-gather of the scores."""
+
+    def __init__(self, local_tokens: torch.Tensor, local_offsets: torch.Tensor, nd_total: int, *, engine=None,
+                 group=None, local_score: Optional[Callable] = None):
+        self.tokens, self.offsets, self.nd_total = local_tokens, local_offsets, nd_total
+        self.engine, self.group = engine, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._local_score = local_score or (lambda q, w: self.engine.maxsim(q, self.tokens, self.offsets, q_weight=w))
+
+    def scores(self, q: torch.Tensor, q_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[nq, nd_total] fp32 on every rank, columns in global document order."""
+        local = self._local_score(q, q_weight)  # [nq, nd_local]
+        if self.world == 1:
+            return local
+        nq = local.shape[0]
+        per = (self.nd_total + self.world - 1) // self.world  # pad every rank's block to the largest
+        send = torch.full((nq, per), float("-inf"), dtype=torch.float32, device=local.device)
+        send[:, : local.shape[1]] = local
+        out = torch.empty(self.world * nq * per, dtype=torch.float32, device=local.device)
+        dist.all_gather_into_tensor(out, send.reshape(-1), group=self.group)
+        blocks = out.view(self.world, nq, per)
+        cols = []
+        for r in range(self.world):
+            lo, hi = shard_bounds(self.nd_total, self.world, r)
+            cols.append(blocks[r, :, : hi - lo])
+        return torch.cat(cols, dim=1)

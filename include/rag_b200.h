@@ -1,0 +1,199 @@
+/*
+ * rag_b200.h — C ABI of the B200-native retrieval-scoring engine.
+ *
+ * This is the drop-in boundary for the two data-parallel scoring stages of
+ * jliang87/Automative-RAG.  Every entry point is `extern "C"`,
+ * takes plain pointers and sizes, never throws, and returns an `int` status
+ * (RS_OK == 0, negative on error; `rs_last_error` gives the text).  All data
+ * pointers are DEVICE pointers owned by the caller unless the name ends in
+ * `_host`; the engine owns only the opaque `rs_handle`.
+ *
+ * Reference interfaces each entry point replaces (paths relative to the
+ * reference checkout):
+ *
+ *   rs_dense_topk / rs_dense_topk_host
+ *       the arithmetic behind QdrantStore.similarity_search_with_score
+ *       (src/core/query/retrieval/vectorstore.py:166-214), i.e. the Qdrant
+ *       cosine / dot search that langchain_qdrant reaches through
+ *       qdrant_client.query_points (vectorstore.py:192-196,202-205,209-212);
+ *       collection created with Distance.COSINE (vectorstore.py:52-57,75-81).
+ *   mask argument of rs_dense_topk
+ *       the predicate QdrantStore._build_filter builds
+ *       (vectorstore.py:216-276), evaluated to one bit per corpus row.
+ *   rs_filter_mask
+ *       evaluates that predicate on device over columnar metadata
+ *       (payload fields indexed at vectorstore.py:89-122).
+ *   rs_maxsim
+ *       ColBERTReranker._compute_maxsim_scores
+ *       (src/core/query/llm/rerankers.py:215-265): matmul :247, row-max :250,
+ *       content-token sum :255-261.  `out_argmax` serves
+ *       _explain_colbert_matches (rerankers.py:489-492).
+ *   rs_rerank_postprocess
+ *       the sort / min-max / 0.8·colbert+0.2·bge blend / [:top_k] tail of
+ *       ColBERTReranker.rerank (rerankers.py:302-343,377-380).
+ *   rs_topk_merge
+ *       has no reference counterpart (the reference is single-GPU); it merges
+ *       per-shard top-k lists after the one all-gather of SURVEY.md §8e.
+ *
+ * Result order everywhere: score descending, ties by ascending id — a valid
+ * refinement of the reference's stable `sorted(..., reverse=True)` for rerank
+ * (rerankers.py:377-380) and of Qdrant's unspecified tie order.
+ *
+ * Threading: one handle per (process, device); calls on one handle must be
+ * serialised by the caller.  Kernels are stream-ordered on the `stream`
+ * argument (a cudaStream_t passed as void*; NULL = legacy default stream).
+ */
+#ifndef RAG_B200_H_
+#define RAG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RS_ABI_VERSION 1
+
+typedef struct rs_handle rs_handle;
+
+/* status codes */
+enum {
+  RS_OK = 0,
+  RS_ERR_INVALID_ARG = -1,   /* NULL pointer, negative size, misaligned buffer ...      */
+  RS_ERR_UNSUPPORTED = -2,   /* shape / dtype outside what the kernels implement          */
+  RS_ERR_CUDA = -3,          /* a CUDA runtime / driver call failed                       */
+  RS_ERR_NO_DEVICE = -4,     /* no sm_100 device visible: there is NO CPU fallback        */
+  RS_ERR_NOMEM = -5
+};
+
+/* element types of embedding buffers */
+enum { RS_F16 = 0, RS_BF16 = 1, RS_F32 = 2 };
+
+/* similarity metrics of the dense stage */
+enum {
+  RS_METRIC_IP = 0,      /* raw inner product                                            */
+  RS_METRIC_COSINE = 1   /* <q/|q|, c/|c|>; |c| from inv_norm[] or assumed 1 when NULL    */
+};
+
+/* which MaxSim kernel family to use (RS_MAXSIM_AUTO picks by shape) */
+enum { RS_MAXSIM_AUTO = 0, RS_MAXSIM_MMA = 1, RS_MAXSIM_TCGEN05 = 2, RS_MAXSIM_SIMT = 3 };
+
+/* which dense kernel family to use (RS_DENSE_AUTO picks by nq) */
+enum { RS_DENSE_AUTO = 0, RS_DENSE_SCAN = 1, RS_DENSE_TCGEN05 = 2 };
+
+int rs_abi_version(void);
+
+/* Create / destroy an engine handle bound to CUDA device `device`.
+ * Fails with RS_ERR_NO_DEVICE when the device is absent or is not compute capability 10.x. */
+int rs_create(int device, rs_handle** out);
+int rs_destroy(rs_handle* h);
+
+/* Text of the last error on this handle (or of the last failed rs_create when h == NULL). */
+const char* rs_last_error(const rs_handle* h);
+
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+int64_t rs_launch_count(const rs_handle* h);
+
+/* Force a kernel family (RS_*_AUTO restores shape-based choice). */
+int rs_set_dense_impl(rs_handle* h, int impl);
+int rs_set_maxsim_impl(rs_handle* h, int impl);
+/* Family used by the most recent rs_dense_topk / rs_maxsim call on this handle. */
+int rs_last_dense_impl(const rs_handle* h);
+int rs_last_maxsim_impl(const rs_handle* h);
+
+/*
+ * Exact brute-force top-k over a row-major corpus [n, d].
+ *
+ *   corpus      [n, d] dtype (RS_F16 | RS_BF16), 16-byte aligned, d % 8 == 0
+ *   inv_norm    [n] fp32 1/|row| or NULL (rows already unit length / metric IP)
+ *   queries     [nq, d] same dtype as corpus
+ *   mask        bit-packed row filter, LSB-first: bit (i & 31) of word (i >> 5) set
+ *               <=> row i passes.  NULL = every row passes.  Query j uses the words
+ *               at mask + j * mask_stride_words (stride 0 = one mask for all queries).
+ *   k           1 <= k <= 2048
+ *   id_base     added to the local row index to form the returned id (shard offset)
+ *   out_scores  [nq, k] fp32, descending; -inf where fewer than k rows pass
+ *   out_ids     [nq, k] int64;  -1 where fewer than k rows pass
+ */
+int rs_dense_topk(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_t dtype,
+                  const float* inv_norm, int32_t metric, const void* queries, int32_t nq,
+                  const uint32_t* mask, int64_t mask_stride_words, int32_t k, int64_t id_base,
+                  float* out_scores, int64_t* out_ids, void* stream);
+
+/* Same search with HOST query / mask / output buffers (the call the Python adapter makes
+ * per request): copies queries (+mask when given) host->device, runs rs_dense_topk on the
+ * handle's stream, copies the k results device->host and synchronises.  The corpus and
+ * inv_norm stay resident on the device.  mask_host may be NULL; mask_dev is used when
+ * mask_host is NULL (either may be NULL = no filter). */
+int rs_dense_topk_host(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_t dtype,
+                       const float* inv_norm, int32_t metric, const void* queries_host,
+                       int32_t nq, const uint32_t* mask_host, const uint32_t* mask_dev,
+                       int64_t mask_stride_words, int32_t k, int64_t id_base,
+                       float* out_scores_host, int64_t* out_ids_host);
+
+/*
+ * Merge `nlists` per-shard top-k lists into one.  Inputs laid out as the all-gather
+ * leaves them: scores/ids [nlists, nq, k_in], list l starting at scores + l * score_list_stride
+ * and ids + l * id_list_stride (strides in ELEMENTS; 0 = dense, i.e. nq * k_in), so the views
+ * into the gathered wire buffer are consumed without a copy.  Entries with id < 0 are padding.
+ * Output [nq, k_out] in (score desc, id asc) order, padded with (-inf, -1).
+ * nlists * k_in <= 16384.
+ */
+int rs_topk_merge(rs_handle* h, const float* scores, const int64_t* ids, int32_t nlists,
+                  int32_t nq, int32_t k_in, int32_t k_out, int64_t score_list_stride,
+                  int64_t id_list_stride, float* out_scores, int64_t* out_ids, void* stream);
+
+/*
+ * ColBERT late-interaction MaxSim.
+ *
+ *   q            [nq, lq, d] dtype
+ *   q_weight     [nq, lq] fp32 per-query-token weight, or NULL for the reference rule
+ *                (rerankers.py:255-261): lq > 2 -> drop token 0 and token lq-1, else all ones
+ *   doc_tokens   [n_tokens, d] dtype, packed;  doc i = rows doc_offsets[i] .. doc_offsets[i+1]
+ *   n_tokens     rows in doc_tokens (>= doc_offsets[nd]); bounds the TMA tensor map
+ *   doc_offsets  [nd + 1] int32 (device), non-decreasing, every doc non-empty
+ *   cand         NULL: every query scores all nd docs (the reference's batch_rerank_queries
+ *                shape, rerankers.py:583-593); else [nq, nc] int32 doc indices per query
+ *   out_scores   [nq, nd] (cand == NULL) or [nq, nc] fp32, in input order
+ *   out_argmax   NULL, or int32 [nq, nd|nc, lq]: index within the doc of the max token
+ *
+ *   score(q, doc) = sum_i w[q,i] * max_j <Q[q,i,:], D[doc,j,:]>,  fp32 accumulation.
+ *   dtype RS_F32 runs an exact-fp32 CUDA-core kernel (small shapes, deployed sizes).
+ */
+int rs_maxsim(rs_handle* h, const void* q, int32_t nq, int32_t lq, int32_t d, int32_t dtype,
+              const float* q_weight, const void* doc_tokens, int64_t n_tokens,
+              const int32_t* doc_offsets, int32_t nd, const int32_t* cand, int32_t nc,
+              float* out_scores, int32_t* out_argmax, void* stream);
+
+/*
+ * Rerank tail (rerankers.py:302-343): per query row of `scores` [nq, n]:
+ *   order by score desc (stable: ties keep input order);
+ *   if other != NULL: min-max normalise scores over the row (all-equal -> 1.0), min-max
+ *   normalise `other` the same way, blend w_a * a + w_b * b, re-sort (stable);
+ *   write the first top_k (index into the input row, final score).
+ *   out_idx [nq, top_k] int32, out_scores [nq, top_k] fp32.   n <= 4096.
+ */
+int rs_rerank_postprocess(rs_handle* h, const float* scores, const float* other, int32_t nq,
+                          int32_t n, float w_a, float w_b, int32_t top_k, int32_t* out_idx,
+                          float* out_scores, void* stream);
+
+/*
+ * Evaluate a _build_filter predicate (vectorstore.py:216-276) over columnar metadata into
+ * the bit-packed mask rs_dense_topk consumes.  The predicate is an AND over `nclauses`
+ * clauses; clause c tests int32 column `cols[c]` ([n], device; keyword fields are
+ * dictionary-encoded by the host) against the value set
+ * `values[val_offsets[c] .. val_offsets[c+1])` (OR within a clause == the nested
+ * Filter(should=[MatchValue...]); a `year` Range(gte=v,lte=v) is the one-element set {v}).
+ * `tombstone` (bit-packed, may be NULL) marks deleted rows, which never pass.
+ *   cols         host array of `nclauses` device pointers
+ *   values       host int32 array;  val_offsets host int32 [nclauses + 1]
+ *   out_mask     device uint32 [ceil(n / 32)]
+ */
+int rs_filter_mask(rs_handle* h, const int32_t* const* cols, int32_t nclauses,
+                   const int32_t* values, const int32_t* val_offsets, const uint32_t* tombstone,
+                   int64_t n, uint32_t* out_mask, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAG_B200_H_ */

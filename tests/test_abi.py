@@ -1,0 +1,52 @@
+"""The C-ABI library loads and exports every symbol include/rag_b200.h declares (CPU: no compute)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import automative_rag_b200 as rag
+from automative_rag_b200 import _ffi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "rag_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rs_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    syms = _declared_symbols()
+    assert len(syms) >= 15
+    lib = ctypes.CDLL(_ffi.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in rag_b200.h but not exported by librag_b200.so"
+        assert s in _ffi.SIGNATURES, f"{s} has no ctypes signature in _ffi.py"
+    assert sorted(_ffi.SIGNATURES) == syms
+
+
+def test_library_loads_and_reports_abi_version():
+    lib = rag.load_library()
+    assert lib.rs_abi_version() == 1
+    m = re.search(r"#define RS_ABI_VERSION (\d+)", open(os.path.join(ROOT, "include", "rag_b200.h")).read())
+    assert int(m.group(1)) == 1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_engine_fails_loudly_without_a_gpu():
+    with pytest.raises(rag.EngineError, match="no CPU fallback"):
+        rag.Engine(0)
+    with pytest.raises(rag.EngineError):
+        rag.B200ColBERTReranker(device="cuda:0")
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "automative-rag_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports oracle/"
