@@ -141,3 +141,14 @@ def compile_filter(flt: Filter, keyword_dicts: Dict[str, Dict[str, int]], int_fi
     if flt.should:
         raise UnsupportedFilter("top-level should")
     return clauses
+
+
+def pack_bits(bits) -> "np.ndarray":
+    """bool [n] -> int32 words [ceil(n/32)], LSB-first: the mask layout rs_dense_topk reads."""
+    import numpy as np
+
+    bits = np.asarray(bits, dtype=np.uint8)
+    n = bits.shape[0]
+    padded = np.zeros((n + 31) // 32 * 32, dtype=np.uint8)
+    padded[:n] = bits
+    return np.packbits(padded.reshape(-1, 32), axis=1, bitorder="little").view("<u4").reshape(-1).view(np.int32).copy()

@@ -30,7 +30,8 @@ import torch
 
 from . import _ffi
 from .documents import Document
-from .filters import (INT_MISSING, FieldCondition, Filter, UnsupportedFilter, build_filter, compile_filter)
+from .filters import (INT_MISSING, FieldCondition, Filter, UnsupportedFilter, build_filter, compile_filter,
+                      pack_bits)
 
 logger = logging.getLogger(__name__)
 
@@ -164,10 +165,7 @@ class Collection:
         import numpy as np
 
         bits = np.fromiter((payload_passes(p, flt) for p in self.payloads[: self.n]), dtype=np.uint8, count=self.n)
-        padded = np.zeros((self.n + 31) // 32 * 32, dtype=np.uint8)
-        padded[: self.n] = bits
-        words = np.packbits(padded.reshape(-1, 32), axis=1, bitorder="little").view("<u4").reshape(-1)
-        mask = torch.from_numpy(words.view(np.int32).copy()).to(self.device)
+        mask = torch.from_numpy(pack_bits(bits)).to(self.device)
         if tomb is not None:
             mask &= ~tomb
         return mask

@@ -1,0 +1,151 @@
+"""MaxSim parity: the three CUDA kernel families (through the C ABI) vs the reference's golden outputs
+and the CPU oracle on identical rounded inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from automative_rag_b200 import _ffi
+from automative_rag_b200.rerankers import pack_documents
+from oracle import maxsim as omaxsim
+from tests._cases import MAXSIM_CASES, make_maxsim_case
+from tests._parity import RTOL_16BIT, RTOL_FP32, assert_scores_close
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name", sorted(MAXSIM_CASES))
+def test_fp32_path_matches_the_reference_golden(engine, name):
+    """Exact-fp32 kernel vs ColBERTReranker._compute_maxsim_scores outputs stored by make_golden.py."""
+    q, docs = make_maxsim_case(MAXSIM_CASES[name])
+    toks, off = pack_documents(docs, engine.device, torch.float32)
+    got = engine.maxsim(q.to(engine.device), toks, off)
+    assert engine.last_maxsim_impl == _ffi.RS_MAXSIM_SIMT
+    want = np.load(os.path.join(GOLD, "maxsim_golden.npz"))[name]
+    assert_scores_close(got[0].cpu().numpy(), want, rtol=RTOL_FP32, atol=1e-3, what=name)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("name", sorted(MAXSIM_CASES))
+def test_mma_path_matches_oracle_on_rounded_inputs(engine, name, dtype):
+    q, docs = make_maxsim_case(MAXSIM_CASES[name])
+    scale = 0.125 if dtype == torch.float16 else 1.0  # keep fp16 products well inside range
+    q16 = (q * scale).to(dtype)
+    d16 = [(d * scale).to(dtype) for d in docs]
+    toks, off = pack_documents(d16, engine.device, dtype)
+    engine.set_maxsim_impl(_ffi.RS_MAXSIM_MMA)
+    try:
+        got, arg = engine.maxsim(q16.to(engine.device), toks, off, want_argmax=True)
+    finally:
+        engine.set_maxsim_impl(_ffi.RS_MAXSIM_AUTO)
+    want, want_arg = omaxsim.maxsim_scores(q16, d16, return_argmax=True)
+    assert_scores_close(got[0].cpu().numpy(), want, rtol=RTOL_16BIT, atol=1e-4, what=name)
+    # argmax: identical except where two doc tokens tie within tolerance
+    ga = arg[0].cpu().numpy()
+    qf = q16[0].float()
+    for j, d in enumerate(d16):
+        sim = (qf @ d.float().T).numpy()
+        rows = np.arange(sim.shape[0])
+        assert ((ga[j] >= 0) & (ga[j] < d.shape[0])).all()
+        np.testing.assert_allclose(sim[rows, ga[j]], sim[rows, want_arg[j]], rtol=RTOL_16BIT, atol=1e-4)
+
+
+def _batch_case(seed, nq, lq, d, lens, dtype):
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(nq, lq, d, generator=g).to(dtype)
+    docs = [torch.randn(n, d, generator=g).to(dtype) for n in lens]
+    return q, docs
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("nq,lq,d,lens", [
+    (4, 32, 128, [300] * 10),                                  # one 128-row tile, docs straddle 256-token tiles
+    (8, 32, 128, [256] * 6),                                   # boundaries exactly on tile edges
+    (9, 32, 128, [1, 2, 31, 32, 33, 255, 256, 257, 511, 513, 700]),  # ragged incl. 1-token docs
+    (64, 32, 64, [180] * 40),                                  # d = 64, many query tiles -> several CTAs per range
+    (5, 20, 128, [64, 100, 300, 17]),                          # lq < 32 -> zero-padded query rows (TMA OOB fill)
+    (6, 45, 128, [90] * 12),                                   # lq in (32, 64] -> two warps per query, atomics
+    (3, 100, 64, [50, 60, 70]),                                # lq in (64, 128]
+    (16, 32, 128, [300] * 300),                                # more docs than SMs / groups
+])
+def test_tcgen05_path_matches_oracle(engine, nq, lq, d, lens, dtype):
+    q, docs = _batch_case(nq * 100 + lq, nq, lq, d, lens, dtype)
+    toks, off = pack_documents(docs, engine.device, dtype)
+    g = torch.Generator().manual_seed(5)
+    w = torch.rand(nq, lq, generator=g)
+    w[:, 0] = 0
+    for weight in (None, w):
+        engine.set_maxsim_impl(_ffi.RS_MAXSIM_TCGEN05)
+        try:
+            got = engine.maxsim(q.to(engine.device), toks, off,
+                                q_weight=None if weight is None else weight.to(engine.device))
+        finally:
+            engine.set_maxsim_impl(_ffi.RS_MAXSIM_AUTO)
+        assert engine.last_maxsim_impl == _ffi.RS_MAXSIM_TCGEN05
+        want = omaxsim.maxsim_scores_packed(q, None if weight is None else weight, torch.cat(docs),
+                                            off.cpu().numpy())
+        assert_scores_close(got.cpu().numpy(), want, rtol=RTOL_16BIT, atol=1e-3, what="tcgen05 maxsim")
+
+
+def test_auto_dispatch_picks_tcgen05_for_shared_candidates(engine):
+    q, docs = _batch_case(1, 8, 32, 128, [100] * 20, torch.bfloat16)
+    toks, off = pack_documents(docs, engine.device, torch.bfloat16)
+    engine.maxsim(q.to(engine.device), toks, off)
+    assert engine.last_maxsim_impl == _ffi.RS_MAXSIM_TCGEN05
+    engine.maxsim(q[:1].to(engine.device), toks, off)  # a single query: general mma.sync kernel
+    assert engine.last_maxsim_impl == _ffi.RS_MAXSIM_MMA
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16])
+def test_candidate_lists_mma_path(engine, dtype):
+    nq, lq, d = 6, 32, 128
+    q, docs = _batch_case(77, nq, lq, d, [50, 120, 300, 7, 64, 200, 33, 90], dtype)
+    toks, off = pack_documents(docs, engine.device, dtype)
+    rng = np.random.default_rng(0)
+    cand = np.stack([rng.permutation(len(docs))[:5] for _ in range(nq)]).astype(np.int32)
+    got = engine.maxsim(q.to(engine.device), toks, off, cand=torch.from_numpy(cand).to(engine.device))
+    assert engine.last_maxsim_impl == _ffi.RS_MAXSIM_MMA
+    want = omaxsim.maxsim_scores_packed(q, None, torch.cat(docs), off.cpu().numpy(), cand)
+    assert_scores_close(got.cpu().numpy(), want, rtol=RTOL_16BIT, atol=1e-3)
+
+
+def test_weights_reproduce_all_three_conventions(engine):
+    """w = [0,1..1,0] == reference HEAD (a4); all-ones == canonical ColBERT / stale test's 32.0; mask-based == a7."""
+    q = torch.ones(1, 32, 64)
+    d = torch.full((5, 64), 1.0 / 64)  # every similarity is exactly 1.0
+    toks, off = pack_documents([d], engine.device, torch.float32)
+    dev = engine.device
+    assert engine.maxsim(q.to(dev), toks, off)[0, 0].item() == 30.0
+    assert engine.maxsim(q.to(dev), toks, off, q_weight=torch.ones(1, 32, device=dev))[0, 0].item() == 32.0
+    m = torch.zeros(1, 32, device=dev)
+    m[0, 1:9] = 1
+    assert engine.maxsim(q.to(dev), toks, off, q_weight=m)[0, 0].item() == 8.0
+
+
+def test_empty_inputs(engine):
+    dev = engine.device
+    q = torch.zeros(1, 4, 64, dtype=torch.float16, device=dev)
+    out = engine.maxsim(q, torch.zeros(1, 64, dtype=torch.float16, device=dev), torch.zeros(1, dtype=torch.int32, device=dev))
+    assert out.shape == (1, 0)
+
+
+def test_config4_full_size_properties(engine):
+    """BASELINE config 4a at full size (256x32 queries vs 1000x300-token shared candidates, bf16):
+    tcgen05 == mma.sync on every (query, doc) pair, and == the CPU oracle on a sample of queries."""
+    nq, lq, d, nd, ld = 256, 32, 128, 1000, 300
+    dev = engine.device
+    g = torch.Generator(device=dev).manual_seed(6)
+    q = torch.randn(nq, lq, d, generator=g, device=dev).to(torch.bfloat16)
+    toks = torch.randn(nd * ld, d, generator=torch.Generator(device=dev).manual_seed(7), device=dev).to(torch.bfloat16)
+    off = (torch.arange(nd + 1, dtype=torch.int32) * ld).to(dev)
+    engine.set_maxsim_impl(_ffi.RS_MAXSIM_TCGEN05)
+    a = engine.maxsim(q, toks, off)
+    engine.set_maxsim_impl(_ffi.RS_MAXSIM_MMA)
+    b = engine.maxsim(q, toks, off)
+    engine.set_maxsim_impl(_ffi.RS_MAXSIM_AUTO)
+    assert_scores_close(a.cpu().numpy(), b.cpu().numpy(), rtol=RTOL_16BIT, atol=1e-3, what="tcgen05 vs mma.sync")
+    sample = [0, 1, 127, 128, 255]
+    want = omaxsim.maxsim_scores_packed(q[sample].cpu(), None, toks.cpu(), off.cpu().numpy())
+    assert_scores_close(a[sample].cpu().numpy(), want, rtol=RTOL_16BIT, atol=1e-3, what="tcgen05 vs oracle")

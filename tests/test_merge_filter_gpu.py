@@ -1,0 +1,118 @@
+"""top-k merge, filter->bitmask and rerank-tail kernels vs the oracle (integer / index work: exact)."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import automative_rag_b200 as rag
+from automative_rag_b200 import distributed as D
+from automative_rag_b200.filters import INT_MISSING
+from oracle import dense as odense
+from oracle import filters as ofilters
+from oracle import maxsim as omaxsim
+from tests._cases import RERANK_CASES, make_rerank_case
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("nl,nq,k_in,k_out", [(1, 1, 10, 10), (2, 3, 10, 10), (8, 5, 100, 100), (8, 2, 1000, 1000),
+                                              (8, 1, 2048, 2048), (4, 7, 33, 50), (3, 2, 5, 2)])
+def test_topk_merge_matches_oracle(engine, nl, nq, k_in, k_out):
+    rng = np.random.default_rng(nl * 1000 + k_in)
+    scores = np.sort(rng.standard_normal((nl, nq, k_in)).astype(np.float32), axis=2)[:, :, ::-1].copy()
+    scores[:, :, ::3] = np.round(scores[:, :, ::3], 1)  # force exact ties across lists
+    scores = np.sort(scores, axis=2)[:, :, ::-1].copy()
+    ids = rng.permutation(nl * nq * k_in).astype(np.int64).reshape(nl, nq, k_in) * 7
+    if k_in > 5:  # padding at the tail of the last list
+        scores[-1, :, -2:] = -np.inf
+        ids[-1, :, -2:] = -1
+    ws, wi = odense.merge_topk(scores, ids, k_out)
+    s, i = engine.topk_merge(torch.from_numpy(scores).to(engine.device), torch.from_numpy(ids).to(engine.device), k_out)
+    np.testing.assert_array_equal(i.cpu().numpy(), wi)
+    np.testing.assert_array_equal(s.cpu().numpy(), ws)
+
+
+def test_topk_merge_consumes_the_gathered_wire_buffer_in_place(engine):
+    nq, k, world = 3, 10, 4
+    rng = np.random.default_rng(0)
+    bufs, all_s, all_i = [], [], []
+    for r in range(world):
+        buf = torch.zeros(D.wire_words(nq, k), dtype=torch.int32)
+        s, i = D.wire_views(buf, nq, k)
+        sv = np.sort(rng.standard_normal((nq, k)).astype(np.float32), axis=1)[:, ::-1].copy()
+        iv = (rng.permutation(nq * k).reshape(nq, k) + r * 1000).astype(np.int64)
+        s.copy_(torch.from_numpy(sv))
+        i.copy_(torch.from_numpy(iv))
+        bufs.append(buf)
+        all_s.append(sv)
+        all_i.append(iv)
+    gathered = torch.cat(bufs).to(engine.device)
+    gs, gi = D.gathered_views(gathered, world, nq, k)
+    s, i = engine.topk_merge(gs, gi, k)
+    ws, wi = odense.merge_topk(np.stack(all_s), np.stack(all_i), k)
+    np.testing.assert_array_equal(i.cpu().numpy(), wi)
+    np.testing.assert_array_equal(s.cpu().numpy(), ws)
+
+
+def _random_payload(rng):
+    md = {}
+    if rng.random() < 0.9:
+        md["manufacturer"] = rng.choice(["Toyota", "Honda", "BMW", "Tesla"])
+    if rng.random() < 0.8:
+        md["year"] = rng.choice([2019, 2020, 2021, 2022, 2023])
+    if rng.random() < 0.7:
+        md["category"] = rng.choice(["sedan", "suv", "truck"])
+    return {"page_content": "x", "metadata": md}
+
+
+@pytest.mark.parametrize("flt", [{"manufacturer": "Toyota"}, {"manufacturer": ["Toyota", "BMW"], "year": 2021},
+                                 {"year": [2019, 2023], "category": "suv"}, {"manufacturer": "Nobody"}, {"year": 2021.5},
+                                 {"manufacturer": "Tesla", "year": 2022, "category": ["suv", "sedan"]}])
+def test_filter_mask_kernel_matches_oracle(engine, flt):
+    from automative_rag_b200.vectorstore import Collection
+
+    rng = random.Random(1)
+    n = 10_007
+    payloads = [_random_payload(rng) for _ in range(n)]
+    col = Collection("t", 8, engine)
+    col.upsert([f"id{i}" for i in range(n)], torch.randn(n, 8), payloads)
+    deleted = np.zeros(n, bool)
+    dele = rng.sample(range(n), 300) + [n - 1, 31, 32]
+    deleted[dele] = True
+    col.delete([f"id{i}" for i in dele])
+    want = ofilters.filter_mask(payloads, flt, deleted)
+    got = col.device_mask(rag.build_filter(flt))
+    got_bits = odense.unpack_mask(got.cpu().numpy().view(np.uint32), n)
+    assert (got_bits == want).all()
+    # the device column encoding itself
+    assert col.columns["year"][:n].cpu().tolist() == [p["metadata"].get("year", INT_MISSING) for p in payloads]
+
+
+def test_filter_on_unindexed_key_uses_host_predicate(engine):
+    from automative_rag_b200.vectorstore import Collection
+
+    n = 500
+    payloads = [{"page_content": "", "metadata": {"custom": i % 3, "manufacturer": "A"}} for i in range(n)]
+    col = Collection("t2", 8, engine)
+    col.upsert([str(i) for i in range(n)], torch.randn(n, 8), payloads)
+    got = col.device_mask(rag.build_filter({"custom": 1}))
+    bits = odense.unpack_mask(got.cpu().numpy().view(np.uint32), n)
+    assert (bits == (np.arange(n) % 3 == 1)).all()
+
+
+@pytest.mark.parametrize("name", sorted(RERANK_CASES))
+def test_rerank_postprocess_kernel_matches_reference_golden(engine, name):
+    """rs_rerank_postprocess vs the reference's own rerank() outputs (tests/golden/rerank_golden.json)."""
+    spec = RERANK_CASES[name]
+    case = make_rerank_case(spec)
+    gold = json.load(open(os.path.join(GOLD, "rerank_golden.json")))[name]["rerank"]
+    scores = omaxsim.maxsim_scores(case["queries"][0], case["docs"])  # fp32 oracle scores as kernel input
+    s = torch.from_numpy(scores).to(engine.device).reshape(1, -1)
+    o = torch.from_numpy(case["bge"]).to(engine.device).reshape(1, -1) if spec["use_bge"] else None
+    idx, out = engine.rerank_postprocess(s, o, spec["top_k"] or s.shape[1])
+    assert idx[0].tolist() == [i for i, _ in gold]
+    np.testing.assert_allclose(out[0].cpu().numpy(), [v for _, v in gold], rtol=1e-5, atol=1e-6)
