@@ -1,0 +1,48 @@
+"""Small driver for ncu: a few launches of each hot kernel at BASELINE sizes.
+
+    python scripts/profile_kernels.py scan      # dense_scan_kernel, 1M x 1024 fp16, top-10
+    python scripts/profile_kernels.py maxsim    # maxsim_tc5_kernel, config 4a
+    python scripts/profile_kernels.py maxsim_mma
+    python scripts/profile_kernels.py dense_batch
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import automative_rag_b200 as rag  # noqa: E402
+from automative_rag_b200 import _ffi  # noqa: E402
+
+what = sys.argv[1] if len(sys.argv) > 1 else "scan"
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+eng = rag.get_engine(0)
+dev = eng.device
+if what == "scan":
+    n, d = 1_000_000, 1024
+    g = torch.Generator(device=dev).manual_seed(1)
+    c = torch.randn(n, d, generator=g, device=dev, dtype=torch.float16)
+    q = torch.randn(d, generator=g, device=dev, dtype=torch.float16)
+    mask = torch.full(((n + 31) // 32,), -1, dtype=torch.int32, device=dev)
+    eng.set_dense_impl(_ffi.RS_DENSE_SCAN)
+    for _ in range(iters):
+        eng.dense_topk(c, q, 10, mask=mask)
+elif what in ("maxsim", "maxsim_mma"):
+    nq, lq, d, nd, ld = 256, 32, 128, 1000, 300
+    g = torch.Generator(device=dev).manual_seed(6)
+    q = torch.randn(nq, lq, d, generator=g, device=dev).bfloat16()
+    toks = torch.randn(nd * ld, d, generator=g, device=dev).bfloat16()
+    off = (torch.arange(nd + 1, dtype=torch.int32) * ld).to(dev)
+    eng.set_maxsim_impl(_ffi.RS_MAXSIM_TCGEN05 if what == "maxsim" else _ffi.RS_MAXSIM_MMA)
+    for _ in range(iters):
+        eng.maxsim(q, toks, off)
+elif what == "dense_batch":
+    n, d, nq, k = 2_000_000, 1024, 1024, 100
+    g = torch.Generator(device=dev).manual_seed(4)
+    c = torch.randn(n, d, generator=g, device=dev, dtype=torch.bfloat16)
+    q = torch.randn(nq, d, generator=g, device=dev, dtype=torch.bfloat16)
+    eng.set_dense_impl(_ffi.RS_DENSE_TCGEN05)
+    for _ in range(iters):
+        eng.dense_topk(c, q, k)
+torch.cuda.synchronize()
+print("ok", what, "launches", eng.launch_count)
