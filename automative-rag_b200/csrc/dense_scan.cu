@@ -6,16 +6,17 @@
 // construction: 2*d bytes per passing row, ~2 flops per byte.
 //
 // Shape of the kernel (B200: 148 SMs, one persistent CTA per SM):
-//   * warp 8 is the TMA producer.  Lane s owns ring stage s: it waits for the stage to be
-//     free, reads the filter bits of the tile, and issues ONE cp.async.bulk for a fully
-//     passing tile (tile = TILE_ROWS consecutive rows = one contiguous byte range) or one
-//     bulk copy per passing row otherwise.  Rows that fail the filter are never read from HBM.
-//   * warps 0..7 are consumers; warp w owns stage w.  A lane reads 16-byte vectors (LDS.128,
-//     conflict free), converts to fp32, FMAs against the query held in registers, and the
-//     warp butterfly-reduces.  8 stages x 16 KB = 128 KB in flight per SM (Little's law for
-//     ~6.5 TB/s x ~1 us needs ~45 KB/SM).
-//   * scores become order-preserving u64 keys and go through the CTA's TopKBuffer; one
-//     barrier per round of 8 tiles decides whether to compact.
+//   * warp 8 is the TMA producer.  It walks the CTA's tiles in order (tile = TILE_ROWS
+//     consecutive rows = one contiguous byte range, 16 KB at d = 1024): lane 0 waits for the
+//     ring slot, then ONE cp.async.bulk moves a fully passing tile, or lane i issues the run of
+//     passing rows starting at row i.  Rows that fail the filter are never read from HBM.
+//   * warps 0..7 are consumers; warp w takes tiles w, w+8, ...  A lane reads 16-byte vectors
+//     (LDS.128, conflict free), converts to fp32, FMAs against the query held in registers, and
+//     the warp butterfly-reduces.  The ring is as deep as shared memory allows (13 x 16 KB =
+//     208 KB at k <= 128): Little's law for ~6.5 TB/s x ~2 us loaded latency needs ~90 KB in
+//     flight per SM, and a slot is out of flight while its tile is being reduced.
+//   * scores become order-preserving u64 keys and go through the CTA's TopKBuffer; a barrier
+//     every few rounds decides whether to compact.
 //   * every CTA writes its sorted top-k to the workspace; the last CTA to finish (atomic
 //     ticket) merges the grid's lists and writes the final (score, id) pairs — no second launch.
 #include "common.cuh"
@@ -25,7 +26,7 @@
 namespace rs {
 
 constexpr int kScanConsumerWarps = 8;
-constexpr int kScanStages = kScanConsumerWarps;
+constexpr int kScanMaxStages = 16;
 constexpr int kScanConsumerThreads = kScanConsumerWarps * 32;
 constexpr int kScanThreads = kScanConsumerThreads + 32;
 constexpr int kConsumerBar = 1;  // named barrier id for the 256 consumer threads
@@ -45,15 +46,16 @@ template <typename T, int NCH>
 __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tile_rows = p.tile_rows;
+  const int S = p.stages;
   const uint32_t row_bytes = (uint32_t)p.d * 2u;
   const uint32_t tile_bytes = row_bytes * tile_rows;
 
   // shared memory carve-up
-  uint8_t* stage_base = smem;                                                        // kScanStages * tile_bytes
-  uint64_t* keys = reinterpret_cast<uint64_t*>(smem + (size_t)kScanStages * tile_bytes);  // [C]
+  uint8_t* stage_base = smem;                                                  // S * tile_bytes
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem + (size_t)S * tile_bytes);  // [C]
   uint64_t* full_bar = keys + p.buf_cap;
-  uint64_t* empty_bar = full_bar + kScanStages;
-  uint64_t* thr = empty_bar + kScanStages;
+  uint64_t* empty_bar = full_bar + kScanMaxStages;
+  uint64_t* thr = empty_bar + kScanMaxStages;
   int* cnt = reinterpret_cast<int*>(thr + 1);
   int* s_flag = cnt + 1;
 
@@ -61,12 +63,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
   const int lane = threadIdx.x & 31;
 
   const int64_t num_tiles = (p.n + tile_rows - 1) / tile_rows;
-  // tiles of this CTA: blockIdx.x, blockIdx.x + grid, ...
+  // tiles of this CTA: blockIdx.x, blockIdx.x + grid, ...  (t-th tile -> global tile blockIdx.x + t * grid)
   const int64_t my_tiles = (num_tiles > blockIdx.x) ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const int64_t rounds = (my_tiles + kScanStages - 1) / kScanStages;
+  const int64_t rounds = (my_tiles + kScanConsumerWarps - 1) / kScanConsumerWarps;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kScanStages; ++s) {
+    for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -78,38 +80,48 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
 
   if (warp == kScanConsumerWarps) {
     // ------------------------------------------------------------------ TMA producer warp
-    if (lane < kScanStages) {
-      const uint64_t pol = policy_evict_first();
-      uint8_t* my_stage = stage_base + (size_t)lane * tile_bytes;
-      const uint32_t all_bits = tile_rows == 32 ? 0xFFFFFFFFu : ((1u << tile_rows) - 1u);
-      int64_t t_local = lane;
-      uint32_t bits = 0;
-      if (t_local < my_tiles) bits = tile_mask_bits(mask, blockIdx.x + t_local * gridDim.x, tile_rows, p.n);
-      for (int64_t r = 0; r < rounds; ++r, t_local += kScanStages) {
-        if (t_local >= my_tiles) break;
-        const int64_t tile = blockIdx.x + t_local * gridDim.x;
-        // prefetch next round's filter bits before blocking on the stage
-        uint32_t bits_next = 0;
-        if (t_local + kScanStages < my_tiles)
-          bits_next = tile_mask_bits(mask, tile + (int64_t)kScanStages * gridDim.x, tile_rows, p.n);
-        mbar_wait(&empty_bar[lane], (uint32_t)((r & 1) ^ 1));
+    // The warp walks this CTA's tiles IN ORDER, converged: lane 0 waits for the ring slot, then
+    // either lane 0 issues one bulk copy for the whole tile or lane i issues the run of passing
+    // rows that starts at row i.  Filter bits are fetched 32 tiles at a time (one per lane), one
+    // batch ahead of their use.
+    const uint64_t pol = policy_evict_first();
+    const uint32_t all_bits = tile_rows == 32 ? 0xFFFFFFFFu : ((1u << tile_rows) - 1u);
+    auto fetch_bits = [&](int64_t t) -> uint32_t {
+      return t < my_tiles ? tile_mask_bits(mask, blockIdx.x + t * gridDim.x, tile_rows, p.n) : 0u;
+    };
+    uint32_t bits_cur = fetch_bits(lane);
+    for (int64_t tb = 0; tb < my_tiles; tb += 32) {
+      const uint32_t bits_nxt = fetch_bits(tb + 32 + lane);
+      const int lim = (int)min((int64_t)32, my_tiles - tb);
+      for (int i = 0; i < lim; ++i) {
+        const int64_t t = tb + i;
+        const uint32_t bits = __shfl_sync(0xFFFFFFFFu, bits_cur, i);
+        const int stage = (int)(t % S);
+        const uint32_t par = (uint32_t)((t / S) & 1);
+        if (lane == 0) mbar_wait(&empty_bar[stage], par ^ 1u);
+        __syncwarp();
+        const int64_t tile = blockIdx.x + t * gridDim.x;
         const uint8_t* src = reinterpret_cast<const uint8_t*>(p.corpus) + (size_t)tile * tile_bytes;
+        uint8_t* dst = stage_base + (size_t)stage * tile_bytes;
         if (bits == 0u) {
-          mbar_arrive(&full_bar[lane]);
+          if (lane == 0) mbar_arrive(&full_bar[stage]);
         } else if (bits == all_bits) {
-          mbar_arrive_expect_tx(&full_bar[lane], tile_bytes);
-          bulk_g2s(my_stage, src, tile_bytes, &full_bar[lane], pol);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&full_bar[stage], tile_bytes);
+            bulk_g2s(dst, src, tile_bytes, &full_bar[stage], pol);
+          }
         } else {
-          mbar_arrive_expect_tx(&full_bar[lane], row_bytes * __popc(bits));
-          uint32_t b = bits;
-          while (b) {
-            int i = __ffs(b) - 1;
-            b &= b - 1;
-            bulk_g2s(my_stage + (size_t)i * row_bytes, src + (size_t)i * row_bytes, row_bytes, &full_bar[lane], pol);
+          if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], row_bytes * __popc(bits));
+          __syncwarp();
+          const bool run_start = ((bits >> lane) & 1u) && (lane == 0 || !((bits >> (lane - 1)) & 1u));
+          if (run_start) {
+            const int run = __ffs(~(bits >> lane)) - 1;  // consecutive passing rows from this one
+            bulk_g2s(dst + (size_t)lane * row_bytes, src + (size_t)lane * row_bytes, row_bytes * run, &full_bar[stage],
+                     pol);
           }
         }
-        bits = bits_next;
       }
+      bits_cur = bits_nxt;
     }
   } else {
     // ------------------------------------------------------------------ consumer warps
@@ -134,22 +146,26 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
     if (p.metric == 1) {
       qss = warp_sum(qss);
       q_scale = qss > 0.f ? rsqrtf(qss) : 0.f;
-      // rsqrtf is approximate (2 ulp); refine once so the scale is fp32-exact to 1 ulp
+      // rsqrtf is approximate (2 ulp); one Newton step makes the scale fp32-accurate
       if (qss > 0.f) q_scale = q_scale * (1.5f - 0.5f * qss * q_scale * q_scale);
     }
     const float* inv_norm = p.inv_norm;
     const int nvec = p.d >> 3;  // 16-byte vectors per row
+    // appends per round <= warps * tile_rows; the buffer tolerates C/2 between checks
+    const int rounds_per_check = max(1, (p.buf_cap >> 1) / (kScanConsumerWarps * tile_rows));
 
-    const uint8_t* my_stage = stage_base + (size_t)warp * tile_bytes;
-    int64_t t_local = warp;
-    for (int64_t r = 0; r < rounds; ++r, t_local += kScanStages) {
-      if (t_local < my_tiles) {
-        const int64_t tile = blockIdx.x + t_local * gridDim.x;
+    int64_t t = warp;
+    for (int64_t r = 0; r < rounds; ++r, t += kScanConsumerWarps) {
+      if (t < my_tiles) {
+        const int stage = (int)(t % S);
+        const uint32_t par = (uint32_t)((t / S) & 1);
+        const uint8_t* my_stage = stage_base + (size_t)stage * tile_bytes;
+        const int64_t tile = blockIdx.x + t * gridDim.x;
         const uint32_t bits = tile_mask_bits(mask, tile, tile_rows, p.n);
         const int64_t row0 = tile * tile_rows;
         float inv = 1.f;
         if (inv_norm != nullptr && lane < tile_rows && ((bits >> lane) & 1u)) inv = __ldg(inv_norm + row0 + lane);
-        mbar_wait(&full_bar[warp], (uint32_t)(r & 1));
+        mbar_wait(&full_bar[stage], par);
         float my_score = 0.f;
         if (bits != 0u) {
           for (int i0 = 0; i0 < tile_rows; i0 += 4) {
@@ -174,14 +190,14 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[warp]);  // stage may be refilled
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);  // slot may be refilled
         // lanes < tile_rows hold one row score each
         const bool live = lane < tile_rows && ((bits >> lane) & 1u);
         const float score = my_score * inv * q_scale;
         const uint64_t key = make_key(score, (uint32_t)(row0 + lane));
         buf.warp_append(live && key > buf.threshold(), key);
       }
-      buf.maybe_compact();
+      if ((r + 1) % rounds_per_check == 0) buf.maybe_compact();
     }
     buf.compact();  // final: keys[0..k) sorted descending (0 = empty)
 
@@ -259,14 +275,25 @@ int scan_tile_rows(int d) {
   return tr;
 }
 
+static size_t scan_fixed_smem(int k) {
+  return (size_t)TopKBuffer::capacity_for(k) * 8 + 2 * kScanMaxStages * 8 + 8 + 16;
+}
+
+int scan_stages(int d, int k) {
+  const size_t tile_bytes = (size_t)scan_tile_rows(d) * d * 2;
+  const size_t budget = 227 * 1024 - 1024;  // leave 1 KB for the runtime's reserved shared memory
+  int s = (int)((budget - scan_fixed_smem(k)) / tile_bytes);
+  return s > kScanMaxStages ? kScanMaxStages : (s < 2 ? 2 : s);
+}
+
 size_t scan_smem_bytes(int d, int k) {
-  const int tr = scan_tile_rows(d);
-  const size_t tile_bytes = (size_t)tr * d * 2;
-  return (size_t)kScanStages * tile_bytes + (size_t)TopKBuffer::capacity_for(k) * 8 + 2 * kScanStages * 8 + 8 + 16;
+  const size_t tile_bytes = (size_t)scan_tile_rows(d) * d * 2;
+  return (size_t)scan_stages(d, k) * tile_bytes + scan_fixed_smem(k);
 }
 
 cudaError_t launch_dense_scan(ScanParams p, int dtype, int num_sms, cudaStream_t stream) {
   p.tile_rows = scan_tile_rows(p.d);
+  p.stages = scan_stages(p.d, p.k);
   p.buf_cap = TopKBuffer::capacity_for(p.k);
   const int64_t num_tiles = (p.n + p.tile_rows - 1) / p.tile_rows;
   int grid = (int)(num_tiles < (int64_t)num_sms ? (num_tiles > 0 ? num_tiles : 1) : num_sms);

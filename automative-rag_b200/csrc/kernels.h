@@ -21,6 +21,7 @@ struct ScanParams {
   float* out_scores;       // [k]
   int64_t* out_ids;        // [k]
   int32_t tile_rows;       // filled by the launcher
+  int32_t stages;          // filled by the launcher
   int32_t buf_cap;         // filled by the launcher
 };
 int scan_tile_rows(int d);

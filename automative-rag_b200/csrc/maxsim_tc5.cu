@@ -197,9 +197,24 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         e2 = (doc + 3 <= d1) ? __ldg(off + doc + 3) - tok0 : INT_MAX;
         if (doc >= d1) e0 = INT_MAX;
       };
+      // One 32-column chunk.  Common case (no document ends inside it): 16 three-input max ops in
+      // 4 independent chains.  Otherwise each segment [a, b) of the chunk is reduced with a
+      // predicated max (static register indexing, no per-column branches) and the document is
+      // finalized ONCE per boundary: the cold path stays small, which matters because an unrolled
+      // per-column version (32 inlined finalize bodies per chunk) made the kernel 24k instructions
+      // and the profile was dominated by instruction-cache misses (stall_no_inst).
       auto consume = [&](const uint32_t (&v)[32], int c0) {
-        if (e0 > c0 + 32) {
-          // no document ends inside this chunk: 16 three-input max ops in 4 independent chains
+        int a = 0;
+        while (e0 <= c0 + 32) {  // warp-uniform
+          const int b = e0 - c0;  // 1..32: the current document ends before column b of this chunk
+          float seg = -CUDART_INF_F;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) seg = fmaxf(seg, (c >= a && c < b) ? __uint_as_float(v[c]) : -CUDART_INF_F);
+          m0 = fmaxf(m0, seg);
+          finalize();
+          a = b;
+        }
+        if (a == 0) {
 #pragma unroll
           for (int c = 0; c < 32; c += 8) {
             m0 = fmaxf(fmaxf(m0, __uint_as_float(v[c + 0])), __uint_as_float(v[c + 1]));
@@ -207,12 +222,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             m2 = fmaxf(fmaxf(m2, __uint_as_float(v[c + 4])), __uint_as_float(v[c + 5]));
             m3 = fmaxf(fmaxf(m3, __uint_as_float(v[c + 6])), __uint_as_float(v[c + 7]));
           }
-        } else {
+        } else if (a < 32) {
+          float seg = -CUDART_INF_F;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            m0 = fmaxf(m0, __uint_as_float(v[c]));
-            if (c0 + c + 1 == e0) finalize();  // warp-uniform
-          }
+          for (int c = 0; c < 32; ++c) seg = fmaxf(seg, (c >= a) ? __uint_as_float(v[c]) : -CUDART_INF_F);
+          m0 = fmaxf(m0, seg);
         }
       };
 
@@ -224,7 +238,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const int cbase = j * kTcBN;
         tmem_ld_32x32(taddr, va);
         tmem_ld_wait(va);
-#pragma unroll
+#pragma unroll 1
         for (int ch = 0; ch < kTcBN / 32; ch += 2) {
           tmem_ld_32x32(taddr + (ch + 1) * 32, vb);  // in flight while chunk ch is reduced
           consume(va, cbase + ch * 32);

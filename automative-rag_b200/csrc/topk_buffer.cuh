@@ -1,6 +1,6 @@
 // topk_buffer.cuh — CTA-level running top-k over a stream of u64 result keys.
 //
-// A shared-memory buffer of C = pow2 >= max(2k, 512) keys plus a threshold (the current
+// A shared-memory buffer of C = pow2 >= max(4k, 512) keys plus a threshold (the current
 // k-th best key).  Producers append only keys above the threshold; when the buffer passes its
 // high-water mark H = C/2 the CTA sorts it (bitonic, descending), keeps the best k and raises
 // the threshold.  The caller guarantees that no more than C - H keys are appended between two
@@ -24,8 +24,11 @@ struct TopKBuffer {
   __device__ __forceinline__ int high_water() const { return C >> 1; }
 
   static __host__ __device__ __forceinline__ int capacity_for(int k) {
+    // 4k: after a compaction (k survivors) there is room for >= k more appends before the next
+    // one, so a scan needs O(log(rows / k)) compactions; 2k would compact every few rows when k is
+    // just under a power of two.
     int c = 512;
-    while (c < 2 * k) c <<= 1;
+    while (c < 4 * k) c <<= 1;
     return c;
   }
 
