@@ -46,8 +46,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Spin until the phase with `parity` completes.  A protocol bug must surface as a CUDA error, not
+// as a hung GPU: after ~2^31 cycles (about a second) of waiting the kernel traps.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3FFu) == 0u && clock64() - t0 > (1ll << 31)) __trap();
   }
 }
 
@@ -72,6 +78,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
           smem_u32(dst_smem)),
       "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
+}
+
+// 128-bit global load for data read exactly once: read-only path, no L1 allocation
+__device__ __forceinline__ uint4 ld_stream(const uint4* ptr) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(ptr));
+  return r;
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -112,23 +127,46 @@ __device__ __forceinline__ float key_score(uint64_t key) { return orderable_f32(
 __device__ __forceinline__ uint32_t key_row(uint64_t key) { return 0xFFFFFFFFu - static_cast<uint32_t>(key); }
 
 // ----------------------------------------------------------------------------- bitonic sort
-// Sort `n_pow2` u64 keys in shared memory, DESCENDING, with `nthreads` threads that all call
-// this function (tid in [0, nthreads)), synchronising on named barrier `bar_id`.
-__device__ __forceinline__ void bitonic_sort_desc(uint64_t* keys, int n_pow2, int tid, int nthreads, int bar_id) {
-  for (int size = 2; size <= n_pow2; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      named_bar_sync(bar_id, nthreads);
-      for (int i = tid; i < (n_pow2 >> 1); i += nthreads) {
-        int lo = 2 * i - (i & (stride - 1));  // index with bit `stride` cleared
-        int hi = lo + stride;
-        bool desc = ((lo & size) == 0);
-        uint64_t a = keys[lo], b = keys[hi];
-        if ((a < b) == desc) {
-          keys[lo] = b;
-          keys[hi] = a;
-        }
-      }
+// Sort `n_pow2` u64 keys in shared memory, DESCENDING, with `nthreads` threads (a multiple of 32)
+// that all call this function (tid in [0, nthreads)), synchronising on named barrier `bar_id`.
+//
+// Compare-exchange stages whose stride is < 64 stay inside a 64-key chunk, so a warp runs all of
+// them on its chunks with __syncwarp only; the CTA barrier is needed just for the strides >= 64.
+// For 512 keys that is ~10 CTA barriers instead of 45 — the sort sits on the critical path of
+// every top-k compaction and of the end-of-kernel merge.
+__device__ __forceinline__ void bitonic_ce(uint64_t* keys, int lo, int stride, int size) {
+  const int hi = lo + stride;
+  const bool desc = ((lo & size) == 0);
+  const uint64_t a = keys[lo], b = keys[hi];
+  if ((a < b) == desc) {
+    keys[lo] = b;
+    keys[hi] = a;
+  }
+}
+// strides stride_hi, stride_hi/2, ..., 1 of the merge step `size`, on every 64-key chunk, warp-locally
+__device__ __forceinline__ void bitonic_local(uint64_t* keys, int n, int size, int stride_hi, int warp, int lane,
+                                              int nwarps) {
+  const int chunk_n = n < 64 ? n : 64;
+  for (int base = warp * 64; base < n; base += nwarps * 64) {
+    for (int stride = stride_hi; stride > 0; stride >>= 1) {
+      __syncwarp();
+      if (lane < (chunk_n >> 1)) bitonic_ce(keys, base + 2 * lane - (lane & (stride - 1)), stride, size);
     }
+    __syncwarp();
+  }
+}
+__device__ __forceinline__ void bitonic_sort_desc(uint64_t* keys, int n_pow2, int tid, int nthreads, int bar_id) {
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+  named_bar_sync(bar_id, nthreads);
+  const int local_max = n_pow2 < 64 ? n_pow2 : 64;
+  for (int size = 2; size <= local_max; size <<= 1) bitonic_local(keys, n_pow2, size, size >> 1, warp, lane, nwarps);
+  for (int size = 128; size <= n_pow2; size <<= 1) {
+    for (int stride = size >> 1; stride >= 64; stride >>= 1) {
+      named_bar_sync(bar_id, nthreads);
+      for (int i = tid; i < (n_pow2 >> 1); i += nthreads) bitonic_ce(keys, 2 * i - (i & (stride - 1)), stride, size);
+    }
+    named_bar_sync(bar_id, nthreads);
+    bitonic_local(keys, n_pow2, size, 32, warp, lane, nwarps);
   }
   named_bar_sync(bar_id, nthreads);
 }
@@ -152,19 +190,36 @@ struct Cvt<__nv_bfloat16> {
   static __device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
 };
 
-// acc += <8 packed 16-bit elements in v, q[0..8)>
+// acc += <8 packed 16-bit elements in v, 8 packed 16-bit elements in q>, fp32 accumulation.
+// sm_100 has a mixed-precision FMA (PTX fma.rn.f32.f16 / .bf16, SASS FHFMA with .H0/.H1 operand
+// selects): a 16-bit x 16-bit product is exact in fp32, so this is bit-identical to converting both
+// operands to fp32 first and costs one instruction per element instead of three.
 template <typename T>
-__device__ __forceinline__ float dot8(const uint4& v, const float* q, float acc) {
-  float2 a = Cvt<T>::unpack(v.x), b = Cvt<T>::unpack(v.y), c = Cvt<T>::unpack(v.z), d = Cvt<T>::unpack(v.w);
-  acc = fmaf(a.x, q[0], acc);
-  acc = fmaf(a.y, q[1], acc);
-  acc = fmaf(b.x, q[2], acc);
-  acc = fmaf(b.y, q[3], acc);
-  acc = fmaf(c.x, q[4], acc);
-  acc = fmaf(c.y, q[5], acc);
-  acc = fmaf(d.x, q[6], acc);
-  acc = fmaf(d.y, q[7], acc);
-  return acc;
+__device__ __forceinline__ float fma16(uint16_t a, uint16_t b, float c);
+template <>
+__device__ __forceinline__ float fma16<__half>(uint16_t a, uint16_t b, float c) {
+  asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(c) : "h"(a), "h"(b));
+  return c;
+}
+template <>
+__device__ __forceinline__ float fma16<__nv_bfloat16>(uint16_t a, uint16_t b, float c) {
+  asm("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(c) : "h"(a), "h"(b));
+  return c;
+}
+template <typename T>
+__device__ __forceinline__ float dot2(uint32_t a, uint32_t b, float acc) {
+  uint16_t al, ah, bl, bh;
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(al), "=h"(ah) : "r"(a));
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(bl), "=h"(bh) : "r"(b));
+  acc = fma16<T>(al, bl, acc);
+  return fma16<T>(ah, bh, acc);
+}
+template <typename T>
+__device__ __forceinline__ float dot8(const uint4& v, const uint4& q, float acc) {
+  acc = dot2<T>(v.x, q.x, acc);
+  acc = dot2<T>(v.y, q.y, acc);
+  acc = dot2<T>(v.z, q.z, acc);
+  return dot2<T>(v.w, q.w, acc);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

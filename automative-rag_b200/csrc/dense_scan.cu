@@ -6,40 +6,59 @@
 // construction: 2*d bytes per passing row, ~2 flops per byte.
 //
 // Shape of the kernel (B200: 148 SMs, one persistent CTA per SM):
-//   * warp 8 is the TMA producer.  It walks the CTA's tiles in order (tile = TILE_ROWS
-//     consecutive rows = one contiguous byte range, 16 KB at d = 1024): lane 0 waits for the
-//     ring slot, then ONE cp.async.bulk moves a fully passing tile, or lane i issues the run of
-//     passing rows starting at row i.  Rows that fail the filter are never read from HBM.
-//   * warps 0..7 are consumers; warp w takes tiles w, w+8, ...  A lane reads 16-byte vectors
-//     (LDS.128, conflict free), converts to fp32, FMAs against the query held in registers, and
-//     the warp butterfly-reduces.  The ring is as deep as shared memory allows (13 x 16 KB =
-//     208 KB at k <= 128): Little's law for ~6.5 TB/s x ~2 us loaded latency needs ~90 KB in
-//     flight per SM, and a slot is out of flight while its tile is being reduced.
+//   * warp 13 is the TMA producer.  The CTA owns mask words b, b+grid, ... (one word = 32
+//     consecutive rows).  The producer turns passing rows into TILES of TILE_ROWS rows (16 KB at
+//     d = 1024) in a shared-memory ring:
+//       - a word with >= 24 of its 32 rows passing is issued as contiguous tiles, ONE
+//         cp.async.bulk each, with the tile's filter bits in the slot so the consumers skip the few
+//         failing rows;
+//       - otherwise the word's passing row ids are appended to a small queue (one parallel step:
+//         lane j places row j at popc(bits below j)) and GATHER slots of TILE_ROWS row ids are
+//         posted from the queue; the consumer warp that takes the slot loads those rows itself with
+//         128-bit streaming loads (2 KB bulk copies measured ~250 cycles each in the TMA unit,
+//         which capped a sparse filter at 30% of its byte roofline).  Every gather slot is full no
+//         matter how sparse the filter is, and rows that fail the filter are never read from HBM.
+//     Each ring slot carries its row ids (or first row + "staged" flag) for the consumers.
+//   * warps 0..S-1 are consumers; warp w owns ring slot w (positions w, w+S, ...).  A lane reads 16-byte
+//     vectors (LDS.128 from the staged tile, conflict free, or LDG.128 for gathered rows),
+//     converts to fp32, FMAs against the query held in registers, and the warp butterfly-reduces.  The ring is as deep as shared memory allows
+//     (13 x 16 KB = 208 KB at k <= 128): Little's law for ~6.5 TB/s x ~2 us loaded latency needs
+//     ~90 KB in flight per SM, and a slot is out of flight while its tile is being reduced.
 //   * scores become order-preserving u64 keys and go through the CTA's TopKBuffer; a barrier
-//     every few rounds decides whether to compact.
+//     every few rounds decides whether to compact.  The stream ends with a padded round and a
+//     round of END markers, so all consumer warps leave the loop in the same round.
 //   * every CTA writes its sorted top-k to the workspace; the last CTA to finish (atomic
 //     ticket) merges the grid's lists and writes the final (score, id) pairs — no second launch.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "topk_buffer.cuh"
 
 namespace rs {
 
-constexpr int kScanConsumerWarps = 8;
-constexpr int kScanMaxStages = 16;
-constexpr int kScanConsumerThreads = kScanConsumerWarps * 32;
-constexpr int kScanThreads = kScanConsumerThreads + 32;
-constexpr int kConsumerBar = 1;  // named barrier id for the 256 consumer threads
+// One consumer warp per ring slot (slot w is always reduced by warp w).  mbarrier waits name a phase
+// by PARITY, which only tells apart the current phase and the one before it; if slots were shared
+// between warps a consumer could wait for a slot's use u+1 before use u has landed and be waved
+// through on stale data (seen on hardware as an intermittent hang).  One owner per slot keeps every
+// waiter at most one phase away from its barrier.
+// A consumer may own two slots (w and w + NW), alternating: while it reduces one tile the other is
+// in flight, so the time a slot spends being reduced stops subtracting from the bytes in flight.
+constexpr int kScanMaxWarps = 13;                  // consumer warps
+constexpr int kScanMaxStages = 2 * kScanMaxWarps;  // ring slots
+constexpr int kScanProducerWarp = kScanMaxWarps;   // warps 0..12 consume, warp 13 produces
+constexpr int kScanThreads = (kScanMaxWarps + 1) * 32;
+constexpr int kConsumerBar = 1;   // named barrier id for the consumer threads
+constexpr int kRowQueue = 128;    // pending passing rows (power of two >= 32 + 32)
+constexpr int kSlotContig = 0x100;  // slot_n flag: rows slot_rows[0] + lane, data staged in the slot by TMA
+                                    // (no flag: a GATHER slot — row ids only, consumers load the rows)
+constexpr int kSlotEnd = -1;
+constexpr int kDenseWordBits = 24;  // words with >= 24 of 32 rows passing are staged whole (<= 25% extra bytes)
 
-__device__ __forceinline__ uint32_t tile_mask_bits(const uint32_t* __restrict__ mask, int64_t tile, int tile_rows,
-                                                   int64_t n) {
-  int64_t row0 = tile * tile_rows;
-  int64_t left = n - row0;
-  uint32_t in_range = left >= tile_rows ? (tile_rows == 32 ? 0xFFFFFFFFu : ((1u << tile_rows) - 1u))
-                                        : ((1u << (int)left) - 1u);
-  if (mask == nullptr) return in_range;
-  uint32_t w = __ldg(mask + (row0 >> 5));  // tile_rows is a power of two <= 32: never straddles a word
-  return (w >> (row0 & 31)) & in_range;
+__device__ __forceinline__ uint64_t policy_evict_normal_() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
 }
 
 template <typename T, int NCH>
@@ -58,14 +77,22 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
   uint64_t* thr = empty_bar + kScanMaxStages;
   int* cnt = reinterpret_cast<int*>(thr + 1);
   int* s_flag = cnt + 1;
+  int* slot_n = s_flag + 1;                                            // [kScanMaxStages]
+  uint32_t* slot_rows = reinterpret_cast<uint32_t*>(slot_n + kScanMaxStages);  // [kScanMaxStages][32]
+  uint32_t* rowq = slot_rows + kScanMaxStages * 32;                    // [kRowQueue]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int NW = p.consumers;           // consumer warps in use; S is a multiple of NW
+  const int consumer_threads = NW * 32;  // consumer warps >= NW have no slot: they leave at once
 
-  const int64_t num_tiles = (p.n + tile_rows - 1) / tile_rows;
-  // tiles of this CTA: blockIdx.x, blockIdx.x + grid, ...  (t-th tile -> global tile blockIdx.x + t * grid)
-  const int64_t my_tiles = (num_tiles > blockIdx.x) ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const int64_t rounds = (my_tiles + kScanConsumerWarps - 1) / kScanConsumerWarps;
+  // Programmatic dependent launch: let the NEXT query's scan (launched with the PDL attribute by
+  // rs_dense_topk's query loop) take over each SM as soon as this CTA leaves it, so its launch,
+  // prologue and first TMA round trip overlap this grid's tail and cross-CTA merge.  Consecutive
+  // scans share nothing but the workspace, which alternates between two buffers; the
+  // griddepcontrol.wait below (before this grid publishes into its buffer) orders grid N+2 after
+  // grid N, the previous user of the same buffer.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -76,70 +103,138 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
   }
   __syncthreads();
 
-  const uint32_t* mask = p.mask;
-
-  if (warp == kScanConsumerWarps) {
+  if (warp == kScanProducerWarp) {
     // ------------------------------------------------------------------ TMA producer warp
-    // The warp walks this CTA's tiles IN ORDER, converged: lane 0 waits for the ring slot, then
-    // either lane 0 issues one bulk copy for the whole tile or lane i issues the run of passing
-    // rows that starts at row i.  Filter bits are fetched 32 tiles at a time (one per lane), one
-    // batch ahead of their use.
-    const uint64_t pol = policy_evict_first();
-    const uint32_t all_bits = tile_rows == 32 ? 0xFFFFFFFFu : ((1u << tile_rows) - 1u);
-    auto fetch_bits = [&](int64_t t) -> uint32_t {
-      return t < my_tiles ? tile_mask_bits(mask, blockIdx.x + t * gridDim.x, tile_rows, p.n) : 0u;
+    const uint64_t pol = p.l2_policy == 0 ? policy_evict_first() : (p.l2_policy == 1 ? policy_evict_normal_() : policy_evict_last());
+    const uint32_t* mask = p.mask;
+    const int64_t num_words = (p.n + 31) >> 5;
+    const int64_t my_words = (num_words > blockIdx.x) ? (num_words - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint8_t* corpus = reinterpret_cast<const uint8_t*>(p.corpus);
+    // Ring cursor, warp-uniform, kept incrementally (no 64-bit div/mod on the issue path):
+    // the next tile goes to slot `slot` in ring pass `phase`; `posmod` = position % NW.
+    int slot = 0, posmod = 0;
+    uint32_t phase = 0;
+    uint32_t head = 0, tail = 0;  // row queue (warp-uniform)
+    const int batch_max = min(S, 8);  // tiles issued per warp pass, one per lane
+
+    auto word_bits = [&](int64_t wi) -> uint32_t {  // filter bits of this CTA's wi-th word
+      if (wi >= my_words) return 0u;
+      const int64_t gw = blockIdx.x + wi * gridDim.x;
+      const int64_t left = p.n - (gw << 5);
+      const uint32_t in_range = left >= 32 ? 0xFFFFFFFFu : ((1u << (int)left) - 1u);
+      return mask ? (__ldg(mask + gw) & in_range) : in_range;
     };
-    uint32_t bits_cur = fetch_bits(lane);
-    for (int64_t tb = 0; tb < my_tiles; tb += 32) {
-      const uint32_t bits_nxt = fetch_bits(tb + 32 + lane);
-      const int lim = (int)min((int64_t)32, my_tiles - tb);
-      for (int i = 0; i < lim; ++i) {
-        const int64_t t = tb + i;
-        const uint32_t bits = __shfl_sync(0xFFFFFFFFu, bits_cur, i);
-        const int stage = (int)(t % S);
-        const uint32_t par = (uint32_t)((t / S) & 1);
-        if (lane == 0) mbar_wait(&empty_bar[stage], par ^ 1u);
-        __syncwarp();
-        const int64_t tile = blockIdx.x + t * gridDim.x;
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.corpus) + (size_t)tile * tile_bytes;
-        uint8_t* dst = stage_base + (size_t)stage * tile_bytes;
-        if (bits == 0u) {
-          if (lane == 0) mbar_arrive(&full_bar[stage]);
-        } else if (bits == all_bits) {
-          if (lane == 0) {
-            mbar_arrive_expect_tx(&full_bar[stage], tile_bytes);
-            bulk_g2s(dst, src, tile_bytes, &full_bar[stage], pol);
+    // Lanes with `active` each claim one ring slot (consecutive slots in lane order) and wait, in
+    // parallel, until its consumer has released it.  The single-lane version of this loop cost
+    // ~600 cycles per tile (mbarrier round trips, 64-bit modulo) and capped the whole kernel.
+    auto claim = [&](bool active, int& stage) {
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, active);
+      const int idx = __popc(m & ((1u << lane) - 1u));
+      const int cnt = __popc(m);
+      stage = slot + idx;
+      uint32_t ph = phase;
+      if (stage >= S) {
+        stage -= S;
+        ph ^= 1u;
+      }
+      if (active) mbar_wait(&empty_bar[stage], ph ^ 1u);
+      slot += cnt;
+      if (slot >= S) {
+        slot -= S;
+        phase ^= 1u;
+      }
+      posmod = (posmod + cnt) % NW;
+    };
+    // lane l < count stages tile (row0 + l * tile_rows) whole if any of its rows pass (bits tb)
+    auto issue_contig = [&](bool active, uint32_t row0, uint32_t tbits) {
+      int stage;
+      claim(active, stage);
+      if (active) {
+        slot_rows[stage * 32] = row0;
+        slot_rows[stage * 32 + 1] = tbits;  // which of the staged rows pass the filter
+        slot_n[stage] = tile_rows | kSlotContig;
+        mbar_arrive_expect_tx(&full_bar[stage], tile_bytes);
+        bulk_g2s(stage_base + (size_t)stage * tile_bytes, corpus + (size_t)row0 * row_bytes, tile_bytes, &full_bar[stage],
+                 pol);
+      }
+      __syncwarp();
+    };
+    // lane l < ntiles posts the ids of queued rows [head + l*nr, head + (l+1)*nr): the consumers LDG them
+    auto issue_gather = [&](int ntiles, int nr) {
+      int stage;
+      const bool active = lane < ntiles;
+      claim(active, stage);
+      if (active) {
+        for (int j = 0; j < nr; ++j) slot_rows[stage * 32 + j] = rowq[(head + lane * nr + j) & (kRowQueue - 1)];
+        slot_n[stage] = nr;
+        mbar_arrive(&full_bar[stage]);
+      }
+      __syncwarp();
+      head += ntiles * nr;
+    };
+    auto issue_marker = [&](int count, int marker) {  // lane l < count posts an empty (0) or END slot
+      int stage;
+      const bool active = lane < count;
+      claim(active, stage);
+      if (active) {
+        slot_n[stage] = marker;
+        mbar_arrive(&full_bar[stage]);
+      }
+      __syncwarp();
+    };
+
+    const uint32_t all_bits = tile_rows == 32 ? 0xFFFFFFFFu : ((1u << tile_rows) - 1u);
+    const int tiles_per_word = 32 / tile_rows;
+    uint32_t bits_cur = word_bits(lane);
+    for (int64_t wb = 0; wb < my_words; wb += 32) {
+      const uint32_t bits_nxt = word_bits(wb + 32 + lane);  // one batch ahead of its use
+      const int lim = (int)min((int64_t)32, my_words - wb);
+      for (int l = 0; l < lim; ++l) {
+        const uint32_t w = __shfl_sync(0xFFFFFFFFu, bits_cur, l);
+        if (w == 0u) continue;
+        const uint32_t row0 = (uint32_t)((blockIdx.x + (wb + l) * gridDim.x) << 5);
+        if (__popc(w) >= kDenseWordBits && (int64_t)row0 + 32 <= p.n) {
+          // (nearly) full word: stage its tiles whole and let the consumers skip the few failing
+          // rows — cheaper than gathering 24+ rows one by one.  Tiles with no passing row are skipped.
+          for (int t0 = 0; t0 < tiles_per_word; t0 += batch_max) {
+            const int t = t0 + lane;
+            const bool in = lane < batch_max && t < tiles_per_word;
+            const uint32_t tb = in ? ((w >> (t * tile_rows)) & all_bits) : 0u;
+            issue_contig(tb != 0u, row0 + t * tile_rows, tb);
           }
         } else {
-          if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], row_bytes * __popc(bits));
+          if ((w >> lane) & 1u) rowq[(tail + __popc(w & ((1u << lane) - 1u))) & (kRowQueue - 1)] = row0 + lane;
+          tail += __popc(w);
           __syncwarp();
-          const bool run_start = ((bits >> lane) & 1u) && (lane == 0 || !((bits >> (lane - 1)) & 1u));
-          if (run_start) {
-            const int run = __ffs(~(bits >> lane)) - 1;  // consecutive passing rows from this one
-            bulk_g2s(dst + (size_t)lane * row_bytes, src + (size_t)lane * row_bytes, row_bytes * run, &full_bar[stage],
-                     pol);
+          int full_tiles = (int)(tail - head) / tile_rows;
+          while (full_tiles > 0) {
+            const int nt = min(full_tiles, batch_max);
+            issue_gather(nt, tile_rows);
+            full_tiles -= nt;
           }
         }
       }
       bits_cur = bits_nxt;
     }
-  } else {
+    if (tail != head) issue_gather(1, (int)(tail - head));
+    while (posmod) issue_marker(min(NW - posmod, batch_max), 0);  // pad the last round
+    for (int left = NW; left > 0; left -= batch_max) issue_marker(min(left, batch_max), kSlotEnd);  // END for all
+  } else if (warp < NW) {
     // ------------------------------------------------------------------ consumer warps
-    TopKBuffer buf{keys, thr, cnt, p.buf_cap, p.k, (int)threadIdx.x, kScanConsumerThreads, kConsumerBar};
+    TopKBuffer buf{keys, thr, cnt, p.buf_cap, p.k, (int)threadIdx.x, consumer_threads, kConsumerBar};
     buf.init();
 
-    // query -> fp32 registers; lane owns elements c*256 + lane*8 + j
-    float q[NCH * 8];
-    const T* qp = reinterpret_cast<const T*>(p.query);
+    // query stays packed 16-bit in registers; lane owns elements c*256 + lane*8 .. +7
+    uint4 q[NCH];
     float qss = 0.f;
+    {
+      const uint4* qv = reinterpret_cast<const uint4*>(p.query);  // 16-byte aligned (checked by the ABI)
+      const int nvq = p.d >> 3;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      int e0 = c * 256 + lane * 8;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float v = (e0 + j < p.d) ? Cvt<T>::to_float(qp[e0 + j]) : 0.f;
-        q[c * 8 + j] = v;
-        qss = fmaf(v, v, qss);
+      for (int c = 0; c < NCH; ++c) {
+        const int vi = c * 32 + lane;
+        q[c] = vi < nvq ? __ldg(qv + vi) : make_uint4(0, 0, 0, 0);
+        qss = dot8<T>(q[c], q[c], qss);
       }
     }
     float q_scale = 1.f;
@@ -152,33 +247,44 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
     const float* inv_norm = p.inv_norm;
     const int nvec = p.d >> 3;  // 16-byte vectors per row
     // appends per round <= warps * tile_rows; the buffer tolerates C/2 between checks
-    const int rounds_per_check = max(1, (p.buf_cap >> 1) / (kScanConsumerWarps * tile_rows));
+    const int rounds_per_check = max(1, (p.buf_cap >> 1) / (NW * tile_rows));
 
-    int64_t t = warp;
-    for (int64_t r = 0; r < rounds; ++r, t += kScanConsumerWarps) {
-      if (t < my_tiles) {
-        const int stage = (int)(t % S);
-        const uint32_t par = (uint32_t)((t / S) & 1);
-        const uint8_t* my_stage = stage_base + (size_t)stage * tile_bytes;
-        const int64_t tile = blockIdx.x + t * gridDim.x;
-        const uint32_t bits = tile_mask_bits(mask, tile, tile_rows, p.n);
-        const int64_t row0 = tile * tile_rows;
+    const bool two_slots = S == 2 * NW;  // this warp alternates between slots warp and warp + NW
+    for (int r = 0;; ++r) {
+      const int stage = warp + ((two_slots && (r & 1)) ? NW : 0);
+      mbar_wait(&full_bar[stage], (uint32_t)((two_slots ? (r >> 1) : r) & 1));
+      const int sn = slot_n[stage];
+      if (sn == kSlotEnd) {  // all consumer warps see END in the same round
+        break;
+      }
+      const int nr = sn & 0xFF;
+      if (nr > 0) {
+        const bool staged = (sn & kSlotContig) != 0;
+        uint32_t row = 0;
+        if (lane < nr) row = staged ? slot_rows[stage * 32] + lane : slot_rows[stage * 32 + lane];
+        const uint32_t tbits = staged ? slot_rows[stage * 32 + 1] : 0xFFFFFFFFu;
+        const bool live = lane < nr && ((tbits >> lane) & 1u);
+        if (!staged) {  // ids are in registers now: the slot can be reused at once
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        }
         float inv = 1.f;
-        if (inv_norm != nullptr && lane < tile_rows && ((bits >> lane) & 1u)) inv = __ldg(inv_norm + row0 + lane);
-        mbar_wait(&full_bar[stage], par);
+        if (inv_norm != nullptr && live) inv = __ldg(inv_norm + row);
         float my_score = 0.f;
-        if (bits != 0u) {
-          for (int i0 = 0; i0 < tile_rows; i0 += 4) {
+        if (staged) {
+          // ---- rows staged in shared memory by TMA
+          const uint8_t* my_stage = stage_base + (size_t)stage * tile_bytes;
+          for (int i0 = 0; i0 < nr; i0 += 4) {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int i = i0 + u;
-              if (i < tile_rows && ((bits >> i) & 1u)) {
+              if (i < nr && ((tbits >> i) & 1u)) {
                 const uint4* rowp = reinterpret_cast<const uint4*>(my_stage + (size_t)i * row_bytes);
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
                   const int v = c * 32 + lane;
-                  if (v < nvec) acc[u] = dot8<T>(rowp[v], &q[c * 8], acc[u]);
+                  if (v < nvec) acc[u] = dot8<T>(rowp[v], q[c], acc[u]);
                 }
               }
             }
@@ -188,53 +294,88 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
               if (lane == i0 + u) my_score = s;
             }
           }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[stage]);  // slot may be refilled
+        } else {
+          // ---- scattered passing rows: 128-bit streaming loads straight from HBM, GR rows in flight
+          constexpr int GR = NCH <= 4 ? 4 : (NCH == 8 ? 2 : 1);  // bounded by the register budget
+          const uint8_t* corpus = reinterpret_cast<const uint8_t*>(p.corpus);
+          for (int i0 = 0; i0 < nr; i0 += GR) {
+            uint4 v[GR][NCH];
+#pragma unroll
+            for (int u = 0; u < GR; ++u) {
+              const uint32_t ru = __shfl_sync(0xFFFFFFFFu, row, min(i0 + u, nr - 1));
+              const uint4* rowp = reinterpret_cast<const uint4*>(corpus + (size_t)ru * row_bytes);
+#pragma unroll
+              for (int c = 0; c < NCH; ++c) {
+                const int vi = c * 32 + lane;
+                v[u][c] = (i0 + u < nr && vi < nvec) ? ld_stream(rowp + vi) : make_uint4(0, 0, 0, 0);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < GR; ++u) {
+              float acc = 0.f;
+#pragma unroll
+              for (int c = 0; c < NCH; ++c) acc = dot8<T>(v[u][c], q[c], acc);
+              const float s = warp_sum(acc);
+              if (lane == i0 + u) my_score = s;
+            }
+          }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[stage]);  // slot may be refilled
-        // lanes < tile_rows hold one row score each
-        const bool live = lane < tile_rows && ((bits >> lane) & 1u);
         const float score = my_score * inv * q_scale;
-        const uint64_t key = make_key(score, (uint32_t)(row0 + lane));
+        const uint64_t key = make_key(score, row);
         buf.warp_append(live && key > buf.threshold(), key);
+      } else {
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
       }
       if ((r + 1) % rounds_per_check == 0) buf.maybe_compact();
     }
     buf.compact();  // final: keys[0..k) sorted descending (0 = empty)
 
     // ------------------------------------------------------------------ cross-CTA merge
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // previous grid fully done (no-op without PDL)
     uint64_t* ws = p.ws_keys + (size_t)blockIdx.x * p.k;
-    for (int i = threadIdx.x; i < p.k; i += kScanConsumerThreads) ws[i] = keys[i];
+    for (int i = threadIdx.x; i < p.k; i += consumer_threads) ws[i] = keys[i];
     __threadfence();
-    named_bar_sync(kConsumerBar, kScanConsumerThreads);
+    named_bar_sync(kConsumerBar, consumer_threads);
     if (threadIdx.x == 0) {
       unsigned ticket = atomicAdd(p.ticket, 1u);
       *s_flag = (ticket == gridDim.x - 1) ? 1 : 0;
     }
-    named_bar_sync(kConsumerBar, kScanConsumerThreads);
+    named_bar_sync(kConsumerBar, consumer_threads);
     if (*s_flag) {
       __threadfence();
       // The buffer already holds this CTA's own top-k with the matching threshold; stream the
-      // other CTAs' sorted lists through it.  Thread t walks list t (+256, ...) J keys at a
-      // time; a list is abandoned at its first key <= threshold (lists are sorted).
-      const int J = max(1, (buf.C >> 1) / kScanConsumerThreads);
-      for (int base = 0; base < (int)gridDim.x; base += kScanConsumerThreads) {
+      // other CTAs' sorted lists through it.  Thread t walks list t (+lists_per_pass, ...); a list is
+      // abandoned at its first key <= threshold (lists are sorted).
+      const int lists_per_pass = min(consumer_threads, buf.C >> 1);  // <= C/2 appends between checks
+      constexpr int KB = 8;  // keys fetched per thread per batch: KB independent L2 loads, one latency
+      for (int base = 0; base < (int)gridDim.x; base += lists_per_pass) {
         const int list = base + threadIdx.x;
-        bool active = list < (int)gridDim.x && list != (int)blockIdx.x;
+        bool active = (int)threadIdx.x < lists_per_pass && list < (int)gridDim.x && list != (int)blockIdx.x;
         const uint64_t* lp = p.ws_keys + (size_t)list * p.k;
-        for (int j0 = 0; j0 < p.k; j0 += J) {
-          for (int j = j0; j < min(j0 + J, p.k); ++j) {
-            uint64_t key = 0ull;
-            if (active) {
-              key = __ldcg(lp + j);
-              if (key <= buf.threshold()) active = false;
+        for (int j0 = 0; j0 < p.k; j0 += KB) {
+          uint64_t kb[KB];
+#pragma unroll
+          for (int u = 0; u < KB; ++u) kb[u] = (active && j0 + u < p.k) ? __ldcg(lp + j0 + u) : 0ull;
+#pragma unroll
+          for (int u = 0; u < KB; ++u) {
+            if (j0 + u < p.k) {  // uniform
+              if (active && kb[u] <= buf.threshold()) active = false;  // sorted list: nothing further can enter
+              buf.warp_append(active, kb[u]);
+              // after the list HEADS the threshold must rise at once (k-th best of own list + all
+              // heads already bounds the answer from below), so compact unconditionally there
+              if (base == 0 && j0 == 0 && u == 0)
+                buf.compact();
+              else
+                buf.maybe_compact();
             }
-            buf.warp_append(active, key);
           }
-          buf.maybe_compact();
+          if (!named_bar_or(kConsumerBar, consumer_threads, active)) break;  // every list exhausted
         }
       }
       buf.compact();
-      for (int i = threadIdx.x; i < p.k; i += kScanConsumerThreads) {
+      for (int i = threadIdx.x; i < p.k; i += consumer_threads) {
         uint64_t key = keys[i];
         if (key == 0ull) {
           p.out_scores[i] = -INFINITY;
@@ -250,15 +391,24 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
 }
 
 template <typename T>
-static cudaError_t launch_scan_t(const ScanParams& p, int grid, size_t smem, cudaStream_t stream) {
+static cudaError_t launch_scan_t(const ScanParams& p, int grid, size_t smem, bool pdl, cudaStream_t stream) {
   const int nch = (p.d + 255) / 256;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kScanThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
 #define RS_SCAN_CASE(N)                                                                                      \
   {                                                                                                          \
     cudaError_t e = cudaFuncSetAttribute(dense_scan_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)smem);                                                         \
     if (e != cudaSuccess) return e;                                                                          \
-    dense_scan_kernel<T, N><<<grid, kScanThreads, smem, stream>>>(p);                                        \
-    return cudaGetLastError();                                                                               \
+    return cudaLaunchKernelEx(&cfg, dense_scan_kernel<T, N>, p);                                             \
   }
   if (nch <= 1) RS_SCAN_CASE(1)
   if (nch <= 2) RS_SCAN_CASE(2)
@@ -268,22 +418,42 @@ static cudaError_t launch_scan_t(const ScanParams& p, int grid, size_t smem, cud
 #undef RS_SCAN_CASE
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 int scan_tile_rows(int d) {
-  int rows = 16384 / (d * 2);
+  // tuning knobs for experiments (scripts/scan_sweep.py); the defaults are the measured optimum
+  static const int tile_bytes_target = env_int("RS_SCAN_TILE_BYTES", 8192);
+  int rows = tile_bytes_target / (d * 2);
   int tr = 1;
   while (tr * 2 <= rows && tr < 32) tr <<= 1;
   return tr;
 }
 
 static size_t scan_fixed_smem(int k) {
-  return (size_t)TopKBuffer::capacity_for(k) * 8 + 2 * kScanMaxStages * 8 + 8 + 16;
+  return (size_t)TopKBuffer::capacity_for(k) * 8 + 2 * kScanMaxStages * 8 + 8 + 16 + kScanMaxStages * 4 +
+         kScanMaxStages * 32 * 4 + kRowQueue * 4;
 }
 
-int scan_stages(int d, int k) {
+// consumers (<= 13) and ring slots (consumers x 1 or x 2) that fit beside the top-k buffer
+static void scan_ring(int d, int k, int& consumers, int& stages) {
+  static const int max_slots = env_int("RS_SCAN_STAGES", kScanMaxStages);
   const size_t tile_bytes = (size_t)scan_tile_rows(d) * d * 2;
   const size_t budget = 227 * 1024 - 1024;  // leave 1 KB for the runtime's reserved shared memory
   int s = (int)((budget - scan_fixed_smem(k)) / tile_bytes);
-  return s > kScanMaxStages ? kScanMaxStages : (s < 2 ? 2 : s);
+  s = s > kScanMaxStages ? kScanMaxStages : s;
+  s = s > max_slots ? max_slots : s;
+  if (s < 2) s = 2;
+  consumers = s < kScanMaxWarps ? s : kScanMaxWarps;
+  stages = consumers * (s / consumers);
+}
+
+int scan_stages(int d, int k) {
+  int c, s;
+  scan_ring(d, k, c, s);
+  return s;
 }
 
 size_t scan_smem_bytes(int d, int k) {
@@ -291,15 +461,17 @@ size_t scan_smem_bytes(int d, int k) {
   return (size_t)scan_stages(d, k) * tile_bytes + scan_fixed_smem(k);
 }
 
-cudaError_t launch_dense_scan(ScanParams p, int dtype, int num_sms, cudaStream_t stream) {
+cudaError_t launch_dense_scan(ScanParams p, int dtype, int num_sms, bool pdl, cudaStream_t stream) {
   p.tile_rows = scan_tile_rows(p.d);
-  p.stages = scan_stages(p.d, p.k);
+  scan_ring(p.d, p.k, p.consumers, p.stages);
   p.buf_cap = TopKBuffer::capacity_for(p.k);
-  const int64_t num_tiles = (p.n + p.tile_rows - 1) / p.tile_rows;
-  int grid = (int)(num_tiles < (int64_t)num_sms ? (num_tiles > 0 ? num_tiles : 1) : num_sms);
+  static const int l2_policy = env_int("RS_SCAN_L2_POLICY", 0);
+  p.l2_policy = l2_policy;
+  const int64_t num_words = (p.n + 31) / 32;  // a CTA owns whole mask words (32 rows)
+  int grid = (int)(num_words < (int64_t)num_sms ? (num_words > 0 ? num_words : 1) : num_sms);
   const size_t smem = scan_smem_bytes(p.d, p.k);
-  if (dtype == 0) return launch_scan_t<__half>(p, grid, smem, stream);
-  return launch_scan_t<__nv_bfloat16>(p, grid, smem, stream);
+  if (dtype == 0) return launch_scan_t<__half>(p, grid, smem, pdl, stream);
+  return launch_scan_t<__nv_bfloat16>(p, grid, smem, pdl, stream);
 }
 
 }  // namespace rs

@@ -21,12 +21,16 @@ struct ScanParams {
   float* out_scores;       // [k]
   int64_t* out_ids;        // [k]
   int32_t tile_rows;       // filled by the launcher
-  int32_t stages;          // filled by the launcher
+  int32_t stages;          // ring slots, filled by the launcher
+  int32_t consumers;       // consumer warps, filled by the launcher (stages is a multiple of it)
   int32_t buf_cap;         // filled by the launcher
+  int32_t l2_policy;       // 0 evict_first (default), 1 normal, 2 evict_last
 };
 int scan_tile_rows(int d);
 size_t scan_smem_bytes(int d, int k);
-cudaError_t launch_dense_scan(ScanParams p, int dtype, int num_sms, cudaStream_t stream);
+// pdl: launch with programmatic stream serialization (only between consecutive scans of one call,
+// whose inputs are all complete before the first launch; see dense_scan.cu)
+cudaError_t launch_dense_scan(ScanParams p, int dtype, int num_sms, bool pdl, cudaStream_t stream);
 
 // ------------------------------------------------------------------ top-k list merge
 cudaError_t launch_topk_merge(const float* scores, const int64_t* ids, int nlists, int nq, int k_in, int k_out,

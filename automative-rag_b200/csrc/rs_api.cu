@@ -21,8 +21,9 @@ struct rs_handle {
   int num_sms = 0;
   cudaStream_t stream = nullptr;  // internal stream of the *_host entry points
   // dense scan workspace
-  uint64_t* ws_keys = nullptr;  // [num_sms, 2048]
-  unsigned* ticket = nullptr;
+  uint64_t* ws_keys = nullptr;  // 2 x [num_sms, 2048]: consecutive scans alternate (they may overlap under PDL)
+  unsigned* ticket = nullptr;   // 2 counters, 128 bytes apart
+  uint64_t scan_seq = 0;
   // *_host staging
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
@@ -129,7 +130,7 @@ int rs_create(int device, rs_handle** out) {
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaMalloc(&h->ws_keys, (size_t)h->num_sms * kMaxK * sizeof(uint64_t));
+  if (e == cudaSuccess) e = cudaMalloc(&h->ws_keys, (size_t)2 * h->num_sms * kMaxK * sizeof(uint64_t));
   if (e == cudaSuccess) e = cudaMalloc(&h->ticket, 256);
   if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, 256);
   if (e != cudaSuccess) {
@@ -223,11 +224,12 @@ int rs_dense_topk(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_
     p.k = k;
     p.metric = metric;
     p.id_base = id_base;
-    p.ws_keys = h->ws_keys;
-    p.ticket = h->ticket;
+    const int buf = (int)(h->scan_seq++ & 1);
+    p.ws_keys = h->ws_keys + (size_t)buf * h->num_sms * kMaxK;
+    p.ticket = h->ticket + buf * 32;
     p.out_scores = out_scores + (size_t)qi * k;
     p.out_ids = out_ids + (size_t)qi * k;
-    cudaError_t e = rs::launch_dense_scan(p, dtype, h->num_sms, st);
+    cudaError_t e = rs::launch_dense_scan(p, dtype, h->num_sms, /*pdl=*/qi > 0, st);
     if (e != cudaSuccess) return cuda_fail(h, e, "dense_scan_kernel launch");
     h->launches += 1;
   }

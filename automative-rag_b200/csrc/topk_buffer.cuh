@@ -59,13 +59,17 @@ struct TopKBuffer {
     }
   }
 
-  // all participating threads; sorts, truncates to k, raises the threshold.
+  // all participating threads; sorts, truncates to k, raises the threshold.  Only the smallest
+  // power-of-two prefix that holds the valid keys is sorted (the final compaction of a scan usually
+  // finds a few dozen keys, not C), and [n, max(n2, k)) is cleared so keys[0..k) never holds stale data.
   __device__ __forceinline__ void compact() {
     named_bar_sync(bar_id, nthreads);
-    int n = min(*reinterpret_cast<volatile int*>(cnt), C);
-    // clear the tail so that stale keys never survive the sort
-    for (int i = n + tid; i < C; i += nthreads) keys[i] = 0ull;
-    bitonic_sort_desc(keys, C, tid, nthreads, bar_id);
+    const int n = min(*reinterpret_cast<volatile int*>(cnt), C);
+    int n2 = 2;
+    while (n2 < n) n2 <<= 1;
+    const int clear_to = max(n2, min(k, C));
+    for (int i = n + tid; i < clear_to; i += nthreads) keys[i] = 0ull;
+    bitonic_sort_desc(keys, n2, tid, nthreads, bar_id);
     if (tid == 0) {
       int kept = min(n, k);
       *cnt = kept;

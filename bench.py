@@ -40,6 +40,12 @@ N_ROWS, DIM, TOPK = 1_000_000, 1024, 10
 METRIC, UNIT = "queries/sec dense top-k (1M x 1024 fp16, top-10, single query, filter bitmask)", "queries/s"
 
 
+def log(*a):
+    """Progress on stderr (stdout carries exactly one JSON line)."""
+    if os.environ.get("BENCH_VERBOSE", "1") != "0":
+        print("[bench]", *a, file=sys.stderr, flush=True)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -239,9 +245,11 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    log(f"rank {rank}/{world}: corpus rows [{lo}, {hi}) resident, warm-up")
     for _ in range(args.warmup):
         step_device()
     barrier()
+    log("timed region")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -261,6 +269,7 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
     qps = nq * args.steps / (elapsed_ms * 1e-3)
+    log(f"value {qps:.1f} q/s; end-to-end leg")
 
     # ---- end to end: per-request host call, H2D + kernel + D2H + sync per query
     out_s = torch.empty(1, k, dtype=torch.float32).pin_memory()
@@ -295,6 +304,7 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
     e2e_qps = nq * e2e_steps / e2e_dt
+    log(f"e2e {e2e_qps:.1f} q/s; sanity check, extras, cpu baseline")
 
     # ---- sanity check of the timed configuration against an independent torch computation on the
     # GPU (not the oracle, not our kernel): fp32 matmul + mask + torch.topk over this rank's shard

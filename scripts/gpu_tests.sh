@@ -6,6 +6,6 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 FILES=${@:-"tests/test_dense_gpu.py tests/test_merge_filter_gpu.py tests/test_maxsim_gpu.py tests/test_dropin_gpu.py"}
 for f in $FILES; do
   name=$(basename $f .py)
-  timeout 600 python -m pytest $f -q -m gpu --timeout 180 -x -q > gpurun_out/$name.log 2>&1
+  timeout ${TEST_TIMEOUT:-240} python -m pytest $f -q -m gpu --timeout 120 -x -q > gpurun_out/$name.log 2>&1
   echo "== $f exit $?"; tail -n 15 gpurun_out/$name.log
 done
