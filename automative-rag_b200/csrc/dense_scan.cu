@@ -7,23 +7,24 @@
 //
 // Shape of the kernel (B200: 148 SMs, one persistent CTA per SM):
 //   * warp 13 is the TMA producer.  The CTA owns mask words b, b+grid, ... (one word = 32
-//     consecutive rows).  The producer turns passing rows into TILES of TILE_ROWS rows (16 KB at
-//     d = 1024) in a shared-memory ring:
+//     consecutive rows).  The producer turns passing rows into TILES of TILE_ROWS rows (4 rows =
+//     8 KB at d = 1024) in a shared-memory ring, up to 8 tiles per warp pass — lane l claims ring
+//     slot l of the pass, waits for it and issues its copies, so the mbarrier round trips of the
+//     pass overlap (a one-lane producer cost ~600 cycles per tile and capped the kernel at 5.7 TB/s):
 //       - a word with >= 24 of its 32 rows passing is issued as contiguous tiles, ONE
 //         cp.async.bulk each, with the tile's filter bits in the slot so the consumers skip the few
 //         failing rows;
-//       - otherwise the word's passing row ids are appended to a small queue (one parallel step:
-//         lane j places row j at popc(bits below j)) and GATHER slots of TILE_ROWS row ids are
-//         posted from the queue; the consumer warp that takes the slot loads those rows itself with
-//         128-bit streaming loads (2 KB bulk copies measured ~250 cycles each in the TMA unit,
-//         which capped a sparse filter at 30% of its byte roofline).  Every gather slot is full no
-//         matter how sparse the filter is, and rows that fail the filter are never read from HBM.
-//     Each ring slot carries its row ids (or first row + "staged" flag) for the consumers.
-//   * warps 0..S-1 are consumers; warp w owns ring slot w (positions w, w+S, ...).  A lane reads 16-byte
-//     vectors (LDS.128 from the staged tile, conflict free, or LDG.128 for gathered rows),
-//     converts to fp32, FMAs against the query held in registers, and the warp butterfly-reduces.  The ring is as deep as shared memory allows
-//     (13 x 16 KB = 208 KB at k <= 128): Little's law for ~6.5 TB/s x ~2 us loaded latency needs
-//     ~90 KB in flight per SM, and a slot is out of flight while its tile is being reduced.
+//       - otherwise the word's passing row ids are appended to a queue (32 words per warp pass:
+//         a shuffle scan of the popcounts gives each lane its offset, then it walks its own set
+//         bits) and GATHER tiles of TILE_ROWS rows are issued from the queue, one bulk copy per run
+//         of consecutive rows.  Every gather tile is full no matter how sparse the filter is, and
+//         rows that fail the filter are never read from HBM.
+//     Each ring slot carries its row ids (or first row + filter bits) for the consumers.
+//   * warps 0..NW-1 are consumers; warp w owns ring slots w and w+NW.  A lane reads 16-byte vectors
+//     of the staged rows (LDS.128, conflict free) and FMAs them against the query, which stays
+//     packed 16-bit in registers (FHFMA: 16-bit x 16-bit -> fp32 accumulate, exact products), and
+//     the warp butterfly-reduces.  The ring is as deep as shared memory allows (26 x 8 KB = 208 KB
+//     at k <= 128); with two slots per consumer one tile is in flight while the other is reduced.
 //   * scores become order-preserving u64 keys and go through the CTA's TopKBuffer; a barrier
 //     every few rounds decides whether to compact.  The stream ends with a padded round and a
 //     round of END markers, so all consumer warps leave the loop in the same round.
@@ -49,9 +50,8 @@ constexpr int kScanMaxStages = 2 * kScanMaxWarps;  // ring slots
 constexpr int kScanProducerWarp = kScanMaxWarps;   // warps 0..12 consume, warp 13 produces
 constexpr int kScanThreads = (kScanMaxWarps + 1) * 32;
 constexpr int kConsumerBar = 1;   // named barrier id for the consumer threads
-constexpr int kRowQueue = 128;    // pending passing rows (power of two >= 32 + 32)
-constexpr int kSlotContig = 0x100;  // slot_n flag: rows slot_rows[0] + lane, data staged in the slot by TMA
-                                    // (no flag: a GATHER slot — row ids only, consumers load the rows)
+constexpr int kRowQueue = 2048;   // pending passing rows (power of two >= 32 words x 32 rows + a tile)
+constexpr int kSlotContig = 0x100;  // slot_n flag: row ids are slot_rows[0] + lane (else slot_rows[lane])
 constexpr int kSlotEnd = -1;
 constexpr int kDenseWordBits = 24;  // words with >= 24 of 32 rows passing are staged whole (<= 25% extra bytes)
 
@@ -159,15 +159,32 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
       }
       __syncwarp();
     };
-    // lane l < ntiles posts the ids of queued rows [head + l*nr, head + (l+1)*nr): the consumers LDG them
+    // Gather tiles: lane (t, j) = (lane / tile_rows, lane % tile_rows) copies queued row
+    // head + t*nr + j into row j of tile t's slot — one bulk copy per RUN of consecutive rows.
+    const int lanes_per_tile_shift = 31 - __clz(tile_rows);
     auto issue_gather = [&](int ntiles, int nr) {
+      const int t = lane >> lanes_per_tile_shift, j = lane & (tile_rows - 1);
+      const bool in = t < ntiles && j < nr;
+      const bool leader = in && j == 0;
       int stage;
-      const bool active = lane < ntiles;
-      claim(active, stage);
-      if (active) {
-        for (int j = 0; j < nr; ++j) slot_rows[stage * 32 + j] = rowq[(head + lane * nr + j) & (kRowQueue - 1)];
+      claim(leader, stage);
+      stage = __shfl_sync(0xFFFFFFFFu, stage, t << lanes_per_tile_shift);
+      const uint32_t row = in ? rowq[(head + t * nr + j) & (kRowQueue - 1)] : 0xFFFFFFFFu;
+      const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, row, 1);
+      const bool start = !in || j == 0 || row != prev + 1u;  // lanes outside a tile terminate runs too
+      const uint32_t starts = __ballot_sync(0xFFFFFFFFu, start);
+      if (in) slot_rows[stage * 32 + j] = row;
+      __syncwarp();
+      if (leader) {
         slot_n[stage] = nr;
-        mbar_arrive(&full_bar[stage]);
+        mbar_arrive_expect_tx(&full_bar[stage], row_bytes * nr);
+      }
+      __syncwarp();
+      if (in && start) {
+        const uint32_t later = lane == 31 ? 0u : (starts >> (lane + 1));
+        const int run = later ? __ffs(later) : (32 - lane);
+        bulk_g2s(stage_base + (size_t)stage * tile_bytes + (size_t)j * row_bytes, corpus + (size_t)row * row_bytes,
+                 row_bytes * run, &full_bar[stage], pol);
       }
       __syncwarp();
       head += ntiles * nr;
@@ -188,30 +205,50 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
     uint32_t bits_cur = word_bits(lane);
     for (int64_t wb = 0; wb < my_words; wb += 32) {
       const uint32_t bits_nxt = word_bits(wb + 32 + lane);  // one batch ahead of its use
-      const int lim = (int)min((int64_t)32, my_words - wb);
-      for (int l = 0; l < lim; ++l) {
-        const uint32_t w = __shfl_sync(0xFFFFFFFFu, bits_cur, l);
-        if (w == 0u) continue;
-        const uint32_t row0 = (uint32_t)((blockIdx.x + (wb + l) * gridDim.x) << 5);
-        if (__popc(w) >= kDenseWordBits && (int64_t)row0 + 32 <= p.n) {
-          // (nearly) full word: stage its tiles whole and let the consumers skip the few failing
-          // rows — cheaper than gathering 24+ rows one by one.  Tiles with no passing row are skipped.
-          for (int t0 = 0; t0 < tiles_per_word; t0 += batch_max) {
-            const int t = t0 + lane;
-            const bool in = lane < batch_max && t < tiles_per_word;
-            const uint32_t tb = in ? ((w >> (t * tile_rows)) & all_bits) : 0u;
-            issue_contig(tb != 0u, row0 + t * tile_rows, tb);
-          }
-        } else {
-          if ((w >> lane) & 1u) rowq[(tail + __popc(w & ((1u << lane) - 1u))) & (kRowQueue - 1)] = row0 + lane;
-          tail += __popc(w);
-          __syncwarp();
-          int full_tiles = (int)(tail - head) / tile_rows;
-          while (full_tiles > 0) {
-            const int nt = min(full_tiles, batch_max);
-            issue_gather(nt, tile_rows);
-            full_tiles -= nt;
-          }
+      // ---- 32 words at once, one per lane
+      const uint32_t w = bits_cur;  // 0 beyond my_words
+      const uint32_t row0 = (uint32_t)((blockIdx.x + (wb + lane) * gridDim.x) << 5);
+      const bool dense = __popc(w) >= kDenseWordBits && (int64_t)row0 + 32 <= p.n;
+      // sparse words: append their passing row ids to the queue (exclusive scan of the popcounts
+      // gives every lane its offset; each lane then walks its own set bits)
+      const int mine = dense ? 0 : __popc(w);
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+      if (mine) {
+        uint32_t qpos = tail + (uint32_t)(incl - mine);
+        uint32_t ww = w;
+        while (ww) {
+          const int bpos = __ffs(ww) - 1;
+          ww &= ww - 1;
+          rowq[(qpos++) & (kRowQueue - 1)] = row0 + bpos;
+        }
+      }
+      tail += (uint32_t)total;
+      __syncwarp();
+      int full_tiles = (int)(tail - head) / tile_rows;
+      while (full_tiles > 0) {
+        const int nt = min(full_tiles, min(batch_max, 32 >> lanes_per_tile_shift));
+        issue_gather(nt, tile_rows);
+        full_tiles -= nt;
+      }
+      // (nearly) full words: stage their tiles whole and let the consumers skip the few failing
+      // rows — cheaper than gathering 24+ rows one by one.  Tiles with no passing row are skipped.
+      uint32_t dense_lanes = __ballot_sync(0xFFFFFFFFu, dense);
+      while (dense_lanes) {
+        const int l = __ffs(dense_lanes) - 1;
+        dense_lanes &= dense_lanes - 1;
+        const uint32_t wl = __shfl_sync(0xFFFFFFFFu, w, l);
+        const uint32_t rl = __shfl_sync(0xFFFFFFFFu, row0, l);
+        for (int t0 = 0; t0 < tiles_per_word; t0 += batch_max) {
+          const int t = t0 + lane;
+          const bool in = lane < batch_max && t < tiles_per_word;
+          const uint32_t tb = in ? ((wl >> (t * tile_rows)) & all_bits) : 0u;
+          issue_contig(tb != 0u, rl + t * tile_rows, tb);
         }
       }
       bits_cur = bits_nxt;
@@ -259,69 +296,38 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
       }
       const int nr = sn & 0xFF;
       if (nr > 0) {
-        const bool staged = (sn & kSlotContig) != 0;
+        const bool contig = (sn & kSlotContig) != 0;
         uint32_t row = 0;
-        if (lane < nr) row = staged ? slot_rows[stage * 32] + lane : slot_rows[stage * 32 + lane];
-        const uint32_t tbits = staged ? slot_rows[stage * 32 + 1] : 0xFFFFFFFFu;
+        if (lane < nr) row = contig ? slot_rows[stage * 32] + lane : slot_rows[stage * 32 + lane];
+        const uint32_t tbits = contig ? slot_rows[stage * 32 + 1] : 0xFFFFFFFFu;
         const bool live = lane < nr && ((tbits >> lane) & 1u);
-        if (!staged) {  // ids are in registers now: the slot can be reused at once
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty_bar[stage]);
-        }
         float inv = 1.f;
         if (inv_norm != nullptr && live) inv = __ldg(inv_norm + row);
         float my_score = 0.f;
-        if (staged) {
-          // ---- rows staged in shared memory by TMA
-          const uint8_t* my_stage = stage_base + (size_t)stage * tile_bytes;
-          for (int i0 = 0; i0 < nr; i0 += 4) {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        // ---- rows staged in shared memory by TMA
+        const uint8_t* my_stage = stage_base + (size_t)stage * tile_bytes;
+        for (int i0 = 0; i0 < nr; i0 += 4) {
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int i = i0 + u;
-              if (i < nr && ((tbits >> i) & 1u)) {
-                const uint4* rowp = reinterpret_cast<const uint4*>(my_stage + (size_t)i * row_bytes);
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                  const int v = c * 32 + lane;
-                  if (v < nvec) acc[u] = dot8<T>(rowp[v], q[c], acc[u]);
-                }
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              float s = warp_sum(acc[u]);
-              if (lane == i0 + u) my_score = s;
-            }
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty_bar[stage]);  // slot may be refilled
-        } else {
-          // ---- scattered passing rows: 128-bit streaming loads straight from HBM, GR rows in flight
-          constexpr int GR = NCH <= 4 ? 4 : (NCH == 8 ? 2 : 1);  // bounded by the register budget
-          const uint8_t* corpus = reinterpret_cast<const uint8_t*>(p.corpus);
-          for (int i0 = 0; i0 < nr; i0 += GR) {
-            uint4 v[GR][NCH];
-#pragma unroll
-            for (int u = 0; u < GR; ++u) {
-              const uint32_t ru = __shfl_sync(0xFFFFFFFFu, row, min(i0 + u, nr - 1));
-              const uint4* rowp = reinterpret_cast<const uint4*>(corpus + (size_t)ru * row_bytes);
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u;
+            if (i < nr && ((tbits >> i) & 1u)) {
+              const uint4* rowp = reinterpret_cast<const uint4*>(my_stage + (size_t)i * row_bytes);
 #pragma unroll
               for (int c = 0; c < NCH; ++c) {
-                const int vi = c * 32 + lane;
-                v[u][c] = (i0 + u < nr && vi < nvec) ? ld_stream(rowp + vi) : make_uint4(0, 0, 0, 0);
+                const int v = c * 32 + lane;
+                if (v < nvec) acc[u] = dot8<T>(rowp[v], q[c], acc[u]);
               }
             }
+          }
 #pragma unroll
-            for (int u = 0; u < GR; ++u) {
-              float acc = 0.f;
-#pragma unroll
-              for (int c = 0; c < NCH; ++c) acc = dot8<T>(v[u][c], q[c], acc);
-              const float s = warp_sum(acc);
-              if (lane == i0 + u) my_score = s;
-            }
+          for (int u = 0; u < 4; ++u) {
+            float s = warp_sum(acc[u]);
+            if (lane == i0 + u) my_score = s;
           }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);  // slot may be refilled
         const float score = my_score * inv * q_scale;
         const uint64_t key = make_key(score, row);
         buf.warp_append(live && key > buf.threshold(), key);
