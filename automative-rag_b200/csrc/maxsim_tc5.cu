@@ -18,8 +18,9 @@
 //     epilogue warp set s drains accumulator s while the tensor core fills the other one.
 //   * warp roles: 0 = TMA producer, 1 = MMA issuer (one elected thread), 2 = TMEM allocator,
 //     4..7 = epilogue set 0, 8..11 = epilogue set 1 (warp % 4 selects the TMEM lane quarter).
-//   * the grid is (document ranges) x (query-tile groups) sized to one wave of the SMs; a CTA's
-//     tiles start at its first document's first token, so document boundaries are the only
+//   * one CTA per SM; the (query-tile group, document) space is cut into equal contiguous spans, a
+//     span into segments at group boundaries (the query tiles are reloaded per segment).  A
+//     segment's tiles start at its first document's first token, so document boundaries are the only
 //     segmentation the epilogue has to track (prefetched two documents ahead).
 #include <cuda.h>
 #include <math_constants.h>
@@ -42,7 +43,7 @@ struct MaxSimTcParams {
   const int32_t* doc_offsets;
   float* out;
   int32_t nq, lq, lq_pad, nd;
-  int32_t num_m_tiles, num_ranges;
+  int32_t num_m_tiles, num_mgroups;
   int32_t accumulate;  // lq_pad > 32: several warps contribute to one (query, doc) -> atomicAdd
 };
 
@@ -66,15 +67,23 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   constexpr uint32_t kABytes = kABytesKH * KH;
   constexpr uint32_t kBBytes = kBBytesKH * KH;
 
-  // ---- work of this CTA
-  const int range = blockIdx.x, mgroup = blockIdx.y;
-  const int d0 = (int)(((int64_t)p.nd * range) / p.num_ranges);
-  const int d1 = (int)(((int64_t)p.nd * (range + 1)) / p.num_ranges);
-  if (d0 >= d1) return;  // uniform: nothing allocated yet
-  const int n_act = min(kTcMG, p.num_m_tiles - mgroup * kTcMG);
-  const int tok0 = __ldg(p.doc_offsets + d0);
-  const int tok1 = __ldg(p.doc_offsets + d1);
-  const int ntiles = (tok1 - tok0 + kTcBN - 1) / kTcBN;
+  // ---- work of this CTA: a contiguous span of the (query group, document) space, cut into
+  // segments at query-group boundaries.  All SMs get the same number of documents (+-1) even when
+  // (groups x ranges) does not divide the SM count.
+  const int64_t units = (int64_t)p.num_mgroups * p.nd;
+  const int64_t u_begin = units * blockIdx.x / gridDim.x;
+  const int64_t u_end = units * (blockIdx.x + 1) / gridDim.x;
+  if (u_begin >= u_end) return;  // uniform: nothing allocated yet
+  struct Seg {
+    int mgroup, d0, d1;
+  };
+  auto seg_at = [&](int64_t u, Seg& sg) -> int64_t {  // segment starting at unit u; returns the next unit
+    sg.mgroup = (int)(u / p.nd);
+    sg.d0 = (int)(u - (int64_t)sg.mgroup * p.nd);
+    const int64_t left = u_end - u;
+    sg.d1 = (int)min((int64_t)p.nd, (int64_t)sg.d0 + left);
+    return u + (sg.d1 - sg.d0);
+  };
 
   // ---- shared memory carve-up (1024-byte aligned: SWIZZLE_128B atoms)
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -82,8 +91,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   uint8_t* smA = sm;                                 // [kTcMG][KH][128 rows x 128 B]
   uint8_t* smB = smA + kTcMG * kABytes;              // [kTcStages][KH][256 rows x 128 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smB + kTcStages * kBBytes);
-  uint64_t* a_full = bars;                 // 1
-  uint64_t* b_full = bars + 1;             // kTcStages
+  uint64_t* a_full = bars;                 // 1: query tiles of the current segment have landed
+  uint64_t* a_empty = bars + 1;            // 1: every MMA of the segment has read them
+  uint64_t* b_full = bars + 2;             // kTcStages
   uint64_t* b_empty = b_full + kTcStages;  // kTcStages
   uint64_t* acc_full = b_empty + kTcStages;  // kTcMG
   uint64_t* acc_empty = acc_full + kTcMG;    // kTcMG
@@ -93,6 +103,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
   if (warp == 0 && lane == 0) {
     mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
     for (int s = 0; s < kTcStages; ++s) {
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
@@ -120,52 +131,83 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       tma_prefetch_desc(&map_q);
       tma_prefetch_desc(&map_d);
       const uint64_t pol = policy_evict_normal();
-      mbar_arrive_expect_tx(a_full, (uint32_t)n_act * kABytes);
-      for (int a = 0; a < n_act; ++a)
-        for (int kh = 0; kh < KH; ++kh)
-          tma_load_3d(smA + a * kABytes + kh * kABytesKH, &map_q, kh * 64, 0, (mgroup * kTcMG + a) * qpt, a_full, pol);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j % kTcStages;
-        const uint32_t ph = (uint32_t)(j / kTcStages) & 1u;
-        mbar_wait(&b_empty[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&b_full[s], kBBytes);
-        for (int kh = 0; kh < KH; ++kh)
-          tma_load_2d(smB + s * kBBytes + kh * kBBytesKH, &map_d, kh * 64, tok0 + j * kTcBN, &b_full[s], pol);
+      int j = 0;  // B tiles issued so far (ring position)
+      int seg_i = 0;
+      Seg sg;
+      for (int64_t u = u_begin; u < u_end; ++seg_i) {
+        u = seg_at(u, sg);
+        const int n_act = min(kTcMG, p.num_m_tiles - sg.mgroup * kTcMG);
+        const int tok0 = __ldg(p.doc_offsets + sg.d0);
+        const int ntiles = (__ldg(p.doc_offsets + sg.d1) - tok0 + kTcBN - 1) / kTcBN;
+        mbar_wait(a_empty, ((uint32_t)seg_i & 1u) ^ 1u);  // previous segment's MMAs are done with A
+        mbar_arrive_expect_tx(a_full, (uint32_t)n_act * kABytes);
+        for (int a = 0; a < n_act; ++a)
+          for (int kh = 0; kh < KH; ++kh)
+            tma_load_3d(smA + a * kABytes + kh * kABytesKH, &map_q, kh * 64, 0, (sg.mgroup * kTcMG + a) * qpt, a_full,
+                        pol);
+        for (int t = 0; t < ntiles; ++t, ++j) {
+          const int s = j % kTcStages;
+          const uint32_t ph = (uint32_t)(j / kTcStages) & 1u;
+          mbar_wait(&b_empty[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&b_full[s], kBBytes);
+          for (int kh = 0; kh < KH; ++kh)
+            tma_load_2d(smB + s * kBBytes + kh * kBBytesKH, &map_d, kh * 64, tok0 + t * kTcBN, &b_full[s], pol);
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(BF16, 128, kTcBN);
-      mbar_wait(a_full, 0);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j % kTcStages;
-        const uint32_t ph = (uint32_t)(j / kTcStages) & 1u;
-        mbar_wait(&b_full[s], ph);
-        tc5_fence_after();
-        for (int a = 0; a < n_act; ++a) {
-          mbar_wait(&acc_empty[a], ((uint32_t)j & 1u) ^ 1u);
+      int j = 0;
+      int uses[kTcMG] = {0, 0};  // accumulator uses so far (phase of acc_empty / acc_full)
+      int seg_i = 0;
+      Seg sg;
+      for (int64_t u = u_begin; u < u_end; ++seg_i) {
+        u = seg_at(u, sg);
+        const int n_act = min(kTcMG, p.num_m_tiles - sg.mgroup * kTcMG);
+        const int tok0 = __ldg(p.doc_offsets + sg.d0);
+        const int ntiles = (__ldg(p.doc_offsets + sg.d1) - tok0 + kTcBN - 1) / kTcBN;
+        mbar_wait(a_full, (uint32_t)seg_i & 1u);
+        for (int t = 0; t < ntiles; ++t, ++j) {
+          const int s = j % kTcStages;
+          const uint32_t ph = (uint32_t)(j / kTcStages) & 1u;
+          mbar_wait(&b_full[s], ph);
           tc5_fence_after();
+          for (int a = 0; a < n_act; ++a) {
+            mbar_wait(&acc_empty[a], ((uint32_t)uses[a] & 1u) ^ 1u);
+            ++uses[a];
+            tc5_fence_after();
 #pragma unroll
-          for (int kh = 0; kh < KH; ++kh) {
-            const uint64_t da = umma_smem_desc_sw128(smem_u32(smA + a * kABytes + kh * kABytesKH));
-            const uint64_t db = umma_smem_desc_sw128(smem_u32(smB + s * kBBytes + kh * kBBytesKH));
+            for (int kh = 0; kh < KH; ++kh) {
+              const uint64_t da = umma_smem_desc_sw128(smem_u32(smA + a * kABytes + kh * kABytesKH));
+              const uint64_t db = umma_smem_desc_sw128(smem_u32(smB + s * kBBytes + kh * kBBytesKH));
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)  // 4 x UMMA_K(16 elements = 32 B) per 128-byte swizzle row
-              umma_f16_ss(tmem_base + (uint32_t)a * kTcBN, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
-                          (kh | kk) != 0 ? 1u : 0u);
+              for (int kk = 0; kk < 4; ++kk)  // 4 x UMMA_K(16 elements = 32 B) per 128-byte swizzle row
+                umma_f16_ss(tmem_base + (uint32_t)a * kTcBN, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
+                            (kh | kk) != 0 ? 1u : 0u);
+            }
+            umma_commit(&acc_full[a]);  // accumulator a ready for its epilogue set
           }
-          umma_commit(&acc_full[a]);  // accumulator a ready for its epilogue set
+          umma_commit(&b_empty[s]);  // B stage reusable once both MMAs have read it
         }
-        umma_commit(&b_empty[s]);  // B stage reusable once both MMAs have read it
+        umma_commit(a_empty);  // query tiles reusable once every MMA of the segment has completed
       }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue sets
     const int set = (warp - 4) >> 2;
     const int quarter = warp & 3;  // TMEM lanes 32*quarter .. +31
-    if (set < n_act) {
-      const int mt = mgroup * kTcMG + set;
+    int use = 0;                   // uses of this set's accumulator so far (phase of acc_full)
+    Seg sg;
+    for (int64_t u = u_begin; u < u_end;) {
+      u = seg_at(u, sg);
+      const int n_act = min(kTcMG, p.num_m_tiles - sg.mgroup * kTcMG);
+      if (set >= n_act) continue;  // this set's query tile does not exist in this group
+      const int d0 = sg.d0, d1 = sg.d1;
+      const int tok0 = __ldg(p.doc_offsets + d0);
+      const int ntiles = (__ldg(p.doc_offsets + d1) - tok0 + kTcBN - 1) / kTcBN;
+      const int mt = sg.mgroup * kTcMG + set;
       const int row = quarter * 32 + lane;           // row in the 128-row tile
       const int query = mt * qpt + row / p.lq_pad;   // uniform across the warp (lq_pad % 32 == 0)
       const int tok = row % p.lq_pad;
@@ -232,8 +274,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)set * kTcBN;
       uint32_t va[32], vb[32];
-      for (int j = 0; j < ntiles; ++j) {
-        mbar_wait(&acc_full[set], (uint32_t)j & 1u);
+      for (int j = 0; j < ntiles; ++j, ++use) {
+        mbar_wait(&acc_full[set], (uint32_t)use & 1u);
         tc5_fence_after();
         const int cbase = j * kTcBN;
         tmem_ld_32x32(taddr, va);
@@ -357,9 +399,8 @@ int tc5_maxsim(Tc5State* s, const MaxSimParams& p, int dtype, cudaStream_t strea
   const int qpt = 128 / lq_pad;
   const int num_m_tiles = (p.nq + qpt - 1) / qpt;
   const int mgroups = (num_m_tiles + kTcMG - 1) / kTcMG;
-  int ranges = s->num_sms / mgroups;
-  if (ranges < 1) ranges = 1;
-  if (ranges > p.nd) ranges = p.nd;
+  long long grid_ll = (long long)mgroups * p.nd;  // one CTA per SM, never more CTAs than work units
+  const int grid_x = (int)(grid_ll < s->num_sms ? grid_ll : s->num_sms);
 
   CUtensorMap map_q, map_d;
   {
@@ -383,7 +424,7 @@ int tc5_maxsim(Tc5State* s, const MaxSimParams& p, int dtype, cudaStream_t strea
   kp.lq_pad = lq_pad;
   kp.nd = p.nd;
   kp.num_m_tiles = num_m_tiles;
-  kp.num_ranges = ranges;
+  kp.num_mgroups = mgroups;
   kp.accumulate = lq_pad > 32 ? 1 : 0;
   if (kp.accumulate) {
     cudaError_t e = cudaMemsetAsync(p.out_scores, 0, (size_t)p.nq * p.nd * sizeof(float), stream);
@@ -394,7 +435,7 @@ int tc5_maxsim(Tc5State* s, const MaxSimParams& p, int dtype, cudaStream_t strea
   }
   const int kh = p.d / 64;
   const size_t smem = 1024 + (size_t)kTcMG * 128 * 128 * kh + (size_t)kTcStages * kTcBN * 128 * kh + 256;
-  dim3 grid(ranges, mgroups);
+  dim3 grid(grid_x);
   cudaError_t e = cudaSuccess;
 #define RS_TC_LAUNCH(BF, KHV)                                                                                         \
   {                                                                                                                   \

@@ -404,6 +404,35 @@ def extra_measurements(eng, corpus, queries, dev, hbm_peak, peaks):
         ms = timed(lambda: eng.dense_topk(corpus, queries[:1], kk), 30)
         out[f"dense_k{kk}"] = {"ms_per_query": ms, "queries_per_s": 1e3 / ms}
 
+    # BASELINE config 3: 1024 queries x 10M x 1024 bf16, top-100 — tcgen05 GEMM + fused per-query top-k
+    try:
+        del corpus
+        torch.cuda.empty_cache()
+        n3, nq3, k3 = 10_000_000, 1024, 100
+        c3 = torch.empty(n3, DIM, dtype=torch.bfloat16, device=dev)
+        g3 = torch.Generator(device=dev).manual_seed(4)
+        for lo in range(0, n3, 500_000):
+            blk = torch.randn(500_000, DIM, generator=g3, device=dev)
+            c3[lo: lo + 500_000] = (blk / blk.norm(dim=1, keepdim=True)).bfloat16()
+        del blk
+        q3 = torch.randn(nq3, DIM, generator=torch.Generator(device=dev).manual_seed(5), device=dev)
+        q3 = (q3 / q3.norm(dim=1, keepdim=True)).bfloat16()
+        eng.set_dense_impl(_ffi.RS_DENSE_TCGEN05)
+        ms = timed(lambda: eng.dense_topk(c3, q3, k3), 5, warm=2)
+        fl = 2.0 * nq3 * n3 * DIM
+        tf_sus = peaks.get("bf16_tflops_sustained", 1400.0)
+        out["dense_batch_config3"] = {
+            "ms_per_batch": ms, "queries_per_s": nq3 / ms * 1e3, "rows": n3, "queries": nq3, "k": k3,
+            "roofline": {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": tf_sus, "unit": "TFLOP/s",
+                         "frac": fl / ms / 1e9 / tf_sus, "traffic": None,
+                         "peak_source": "measured sustained" if "bf16_tflops_sustained" in peaks else "fallback"}}
+        del c3
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out["dense_batch_config3"] = {"error": str(e)}
+    finally:
+        eng.set_dense_impl(_ffi.RS_DENSE_SCAN)
+
     # MaxSim config 4a: 256 queries x 32 tokens vs 1000 shared candidates x 300 tokens, d=128, bf16
     nq, lq, d, nd, ld = 256, 32, 128, 1000, 300
     g = torch.Generator(device=dev).manual_seed(6)
