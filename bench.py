@@ -330,8 +330,11 @@ def run_b200(args):
     scan_launches = nq * args.steps
     avg_launch_ms = elapsed_ms / scan_launches  # launches are back to back on one stream
     achieved = alg_bytes / (avg_launch_ms * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this exact workload from the committed
+    # `ncu --set full` capture (profiles/r01_dense_scan_v3_ncu.txt): 2.048237 GB + 4.47 MB; null for other shapes
+    traffic = 2_052_708_808 if (world == 1 and args.rows == N_ROWS and k == TOPK and args.mask_p >= 1.0) else None
     roofline = {"bound": "hbm", "kernel": "dense_scan_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": avg_launch_ms * 1e3}
 
     extra = {}
