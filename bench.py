@@ -436,6 +436,37 @@ def extra_measurements(eng, corpus, queries, dev, hbm_peak, peaks):
     finally:
         eng.set_dense_impl(_ffi.RS_DENSE_SCAN)
 
+    # BASELINE config 1: the reference's own call shape — 1 query x 32 tokens vs 100 docs x 180 tokens, d=128,
+    # fp32 tensors on the HOST — through the drop-in `_compute_maxsim_scores` (H2D, one kernel, D2H inside the
+    # timed region), next to the CPU port of the reference loop (rerankers.py:244-263) on this box's cores.
+    try:
+        import time as _time
+
+        import automative_rag_b200 as rag
+        from oracle import maxsim as omaxsim
+
+        g1 = torch.Generator().manual_seed(0)
+        q1 = torch.randn(1, 32, 128, generator=g1)
+        d1 = [torch.randn(180, 128, generator=g1) for _ in range(100)]
+        for name, fp16 in (("fp32_exact", False), ("fp16_mma", True)):
+            rr = rag.B200ColBERTReranker(device=str(dev), use_fp16=fp16, use_bge_reranker=False)
+            for _ in range(5):
+                rr._compute_maxsim_scores(q1, d1)
+            t0 = _time.perf_counter()
+            for _ in range(50):
+                rr._compute_maxsim_scores(q1, d1)
+            dt = (_time.perf_counter() - t0) / 50
+            out[f"maxsim_config1_{name}"] = {"ms_per_query_e2e": dt * 1e3, "queries_per_s": 1.0 / dt}
+        omaxsim.maxsim_scores(q1, d1)
+        t0 = _time.perf_counter()
+        for _ in range(20):
+            omaxsim.maxsim_scores(q1, d1)
+        dt = (_time.perf_counter() - t0) / 20
+        out["maxsim_config1_cpu_port"] = {"ms_per_query": dt * 1e3, "queries_per_s": 1.0 / dt,
+                                          "cores": torch.get_num_threads(), "kind": "port"}
+    except Exception as e:  # noqa: BLE001
+        out["maxsim_config1"] = {"error": str(e)}
+
     # MaxSim config 4a: 256 queries x 32 tokens vs 1000 shared candidates x 300 tokens, d=128, bf16
     nq, lq, d, nd, ld = 256, 32, 128, 1000, 300
     g = torch.Generator(device=dev).manual_seed(6)
