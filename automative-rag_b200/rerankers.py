@@ -40,7 +40,12 @@ def pack_documents(doc_embeddings_list: Sequence[torch.Tensor], device: torch.de
             raise ValueError("document with zero tokens")  # torch.max over an empty dim raises in the reference too
         lens.append(d.size(0))
         mats.append(d)
-    tokens = torch.cat([m.to(device=device, dtype=dtype) for m in mats], dim=0).contiguous()
+    if len({(m.device, m.dtype) for m in mats}) == 1:
+        # one concatenation where the tensors live, then ONE transfer / cast (100 small H2D copies cost more
+        # than the scoring kernel itself)
+        tokens = torch.cat(mats, dim=0).to(device=device, dtype=dtype).contiguous()
+    else:
+        tokens = torch.cat([m.to(device=device, dtype=dtype) for m in mats], dim=0).contiguous()
     offs = torch.zeros(len(lens) + 1, dtype=torch.int64)
     offs[1:] = torch.tensor(lens, dtype=torch.int64).cumsum(0)
     if int(offs[-1]) >= 2**31:
