@@ -118,7 +118,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
@@ -246,13 +246,18 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     log(f"rank {rank}/{world}: corpus rows [{lo}, {hi}) resident, warm-up")
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-    log("timed region")
+    # clocks are sampled every 20 ms from the warm-up on (same load as the timed steps): a sharded timed region
+    # can be shorter than one nvidia-smi sampling period
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.15)  # let nvidia-smi come up
+    est_step_s = nq * 3.0e-4 * (args.rows / N_ROWS) / world        # ~300 us per query per 1M rows per GPU
+    warm_steps = max(args.warmup, int(0.3 / max(est_step_s, 1e-4)) + 1)  # >= W steps and >= ~0.3 s of load
+    for _ in range(warm_steps):
+        step_device()
+    barrier()
+    log("timed region")
     launches0 = eng.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -361,8 +366,9 @@ def run_b200(args):
             "dtype": "f16 in / f32 accumulate", "data": "synthetic",
             "config": {"workload": "config2", "rows": args.rows, "rows_per_gpu": rows_local, "dim": DIM, "k": k,
                        "mask_p": args.mask_p, "queries_per_step": nq, "parallelism": f"row-shard x{world}",
-                       "l2": "inputs larger than L2 (2 GB corpus re-read per query vs 126 MB L2)" if rows_local * DIM * 2 > 4 * 126e6
-                             else "shard comparable to L2: see DESIGN.md"},
+                       "warmup_steps_run": warm_steps,
+                       "l2": (f"inputs larger than L2: every query re-reads its {rows_local * DIM * 2 / 1e6:.0f} MB shard "
+                              "(126 MB L2, loads carry an evict_first hint)")},
             "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": nq * DIM * 2, "d2h_bytes_per_step": nq * k * 12,
                     "steps": e2e_steps},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
