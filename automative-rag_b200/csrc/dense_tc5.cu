@@ -17,8 +17,10 @@
 //     (A 2 x 16 KB + B 32 KB per stage).  grid = (corpus ranges) x (query groups), one wave; the
 //     CTAs of one range run side by side so the corpus is read from HBM once and from L2 after that.
 //   * candidates above the threshold go to a per-(CTA, query) buffer in global memory (L2
-//     resident); when a buffer fills, the WARP sorts that query's 256 keys in shared memory and keeps
-//     the best k — expected k*ln(rows/k) appends per query, so this is off the critical path.
+//     resident) with room for a whole tile of appends; at the end of a tile — after the accumulators
+//     have been handed back — the WARP sorts the keys of each query whose buffer passed 192 entries in
+//     shared memory and keeps the best k, raising that query's threshold.  Expected k*ln(rows/k)
+//     appends per query.
 //   * each CTA writes its per-query top-k lists; rs_topk_merge (one more small launch) merges the
 //     ranges.  Result order and tie rule are those of the scan: (score desc, id asc).
 #include <cuda.h>
@@ -39,7 +41,9 @@ constexpr int kDtBN = 256;        // corpus rows per tile (UMMA N)
 constexpr int kDtBK = 64;         // K elements per stage (one 128-byte swizzle row)
 constexpr int kDtMT = 2;          // 128-query UMMA tiles per CTA
 constexpr int kDtStages = 3;
-constexpr int kDtCap = 256;       // candidate buffer entries per (CTA, query); k <= kDtCap / 2
+constexpr int kDtCap = 512;       // candidate buffer entries per (CTA, query): room for a whole tile (256 rows) of
+                                  // appends on top of kDtCompactAt, so compaction can wait for the end of the tile
+constexpr int kDtCompactAt = 192; // compact a query's buffer once it holds more than this (keeps the sort at 256 keys)
 constexpr uint32_t kDtABytes = 128 * 128;      // one 128-row query tile, one K block
 constexpr uint32_t kDtBBytes = kDtBN * 128;    // one 256-row corpus tile, one K block
 constexpr uint32_t kDtStageBytes = kDtMT * kDtABytes + kDtBBytes;
@@ -56,14 +60,14 @@ struct DenseTcParams {
   int32_t num_ranges, tiles_total;
 };
 
-// warp-level bitonic sort of 256 u64 keys in shared memory, descending (one warp, __syncwarp only)
-__device__ __forceinline__ void warp_sort256_desc(uint64_t* keys, int lane) {
-  for (int size = 2; size <= 256; size <<= 1) {
+// warp-level bitonic sort of n (power of two, 64..512) u64 keys in shared memory, descending
+// (one warp, __syncwarp only)
+__device__ __forceinline__ void warp_sort_desc(uint64_t* keys, int n, int lane) {
+  for (int size = 2; size <= n; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       __syncwarp();
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int i = r * 32 + lane;  // 128 pairs
+      for (int r = 0; r < (n >> 6); ++r) {
+        const int i = r * 32 + lane;  // n / 2 pairs
         const int lo = 2 * i - (i & (stride - 1));
         bitonic_ce(keys, lo, stride, size);
       }
@@ -193,12 +197,10 @@ __global__ void __launch_bounds__(kDtThreads, 1)
       auto compact_lane = [&](int L) {
         const uint64_t* src = (const uint64_t*)__shfl_sync(0xFFFFFFFFu, (unsigned long long)my_cand, L);
         const int c = __shfl_sync(0xFFFFFFFFu, cnt, L);
-#pragma unroll
-        for (int r = 0; r < kDtCap / 32; ++r) {
-          const int i = r * 32 + lane;
-          my_sort[i] = i < c ? __ldcg(src + i) : 0ull;
-        }
-        warp_sort256_desc(my_sort, lane);
+        int n2 = 64;
+        while (n2 < c) n2 <<= 1;  // sort only the smallest power of two that holds the valid keys
+        for (int i = lane; i < n2; i += 32) my_sort[i] = i < c ? __ldcg(src + i) : 0ull;
+        warp_sort_desc(my_sort, n2, lane);
         const int kept = min(c, k);
         uint64_t* dst = const_cast<uint64_t*>(src);
         for (int i = lane; i < kept; i += 32) __stcg(dst + i, my_sort[i]);
@@ -248,13 +250,6 @@ __global__ void __launch_bounds__(kDtThreads, 1)
                 }
               }
             }
-            // a buffer that cannot take another 32 appends is compacted now, by the whole warp
-            uint32_t need = __ballot_sync(0xFFFFFFFFu, cnt > kDtCap - 32);
-            while (need) {
-              const int L = __ffs(need) - 1;
-              need &= need - 1;
-              compact_lane(L);
-            }
           }
         };
         tmem_ld_32x32(taddr, va);
@@ -273,6 +268,15 @@ __global__ void __launch_bounds__(kDtThreads, 1)
           }
           consume(vb, ch + 1);
           if (ch + 2 < kDtBN / 32) tmem_ld_wait(va);
+        }
+        // The accumulators went back to the MMA warp above, so compaction runs while the tensor core works on
+        // the next tile.  Done inside the tile it sat on the critical path: the MMA restarts only when ALL
+        // eight warps have drained, and some warp compacts in almost every tile.
+        uint32_t need = __ballot_sync(0xFFFFFFFFu, cnt > kDtCompactAt);
+        while (need) {
+          const int L = __ffs(need) - 1;
+          need &= need - 1;
+          compact_lane(L);
         }
       }
       // ---- final: every query's buffer sorted, best k written as (score, id) lists of this range
@@ -315,7 +319,7 @@ bool tc5_dense_supported(const Tc5State* s, int64_t n, int d, int nq, int k, con
   if (!s) return false;
   if (nq < 32 || n < kDtBN) return false;        // below that the scan loop is the better tool
   if (d % kDtBK != 0 || d < kDtBK) return false;
-  if (k > kDtCap / 2) return false;
+  if (k > 128) return false;
   if (mask_stride_words != 0) return false;      // one shared filter for the batch
   if (n >= (1ll << 31) * (int64_t)1) return false;
   return true;

@@ -25,7 +25,8 @@ struct rs_handle {
   unsigned* ticket = nullptr;   // 2 counters, 128 bytes apart
   uint64_t scan_seq = 0;
   // *_host staging
-  void* pinned = nullptr;
+  void* pinned = nullptr;      // mapped pinned memory: staged inputs, and results written by the kernel itself
+  void* pinned_dev = nullptr;  // device alias of `pinned`
   size_t pinned_bytes = 0;
   void* dev_stage = nullptr;
   size_t dev_stage_bytes = 0;
@@ -81,8 +82,9 @@ int ensure_staging(rs_handle* h, size_t host_bytes, size_t dev_bytes) {
     h->pinned = nullptr;
     h->pinned_bytes = 0;
     size_t want = host_bytes < (1u << 20) ? (1u << 20) : host_bytes;
-    cudaError_t e = cudaMallocHost(&h->pinned, want);
-    if (e != cudaSuccess) return cuda_fail(h, e, "cudaMallocHost(staging)");
+    cudaError_t e = cudaHostAlloc(&h->pinned, want, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer(&h->pinned_dev, h->pinned, 0);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaHostAlloc(staging)");
     h->pinned_bytes = want;
   }
   if (dev_bytes > h->dev_stage_bytes) {
@@ -262,13 +264,14 @@ int rs_dense_topk_host(rs_handle* h, const void* corpus, int64_t n, int32_t d, i
   cudaError_t e = cudaMemcpyAsync(dp, hp, q_bytes + m_bytes, cudaMemcpyHostToDevice, h->stream);
   if (e != cudaSuccess) return cuda_fail(h, e, "H2D(queries, mask)");
   const uint32_t* mask = mask_host ? reinterpret_cast<const uint32_t*>(dp + q_bytes) : mask_dev;
-  float* d_scores = reinterpret_cast<float*>(dp + q_bytes + m_bytes);
-  int64_t* d_ids = reinterpret_cast<int64_t*>(dp + q_bytes + m_bytes + os_bytes);
+  // The k result pairs are written by the kernel straight into mapped pinned memory: no device-to-host copy to
+  // enqueue and wait for, the stream synchronise below is the only round trip after the launch.
+  uint8_t* hp_dev = static_cast<uint8_t*>(h->pinned_dev);
+  float* d_scores = reinterpret_cast<float*>(hp_dev + q_bytes + m_bytes);
+  int64_t* d_ids = reinterpret_cast<int64_t*>(hp_dev + q_bytes + m_bytes + os_bytes);
   rc = rs_dense_topk(h, corpus, n, d, dtype, inv_norm, metric, dp, nq, mask, mask_stride_words, k, id_base, d_scores,
                      d_ids, h->stream);
   if (rc != RS_OK) return rc;
-  e = cudaMemcpyAsync(hp + q_bytes + m_bytes, dp + q_bytes + m_bytes, os_bytes + oi_bytes, cudaMemcpyDeviceToHost, h->stream);
-  if (e != cudaSuccess) return cuda_fail(h, e, "D2H(results)");
   e = cudaStreamSynchronize(h->stream);
   if (e != cudaSuccess) return cuda_fail(h, e, "rs_dense_topk_host: stream synchronize");
   memcpy(out_scores_host, hp + q_bytes + m_bytes, (size_t)nq * k * 4);

@@ -494,6 +494,23 @@ def extra_measurements(eng, corpus, queries, dev, hbm_peak, peaks):
             out[f"maxsim_4a_{name}"] = {"error": str(e)}
         finally:
             eng.set_maxsim_impl(_ffi.RS_MAXSIM_AUTO)
+    # BASELINE config 4b: per-query candidate lists (the retrieve-then-rerank shape): 256 queries, each with its
+    # own 1000 documents drawn from a 20000-document pool (1.5 GB of bf16 tokens, 12x the L2) -> HBM-bound:
+    # 256 * 1000 * 300 * 128 * 2 B = 19.66 GB of token reads per batch.  Runs on the general mma.sync kernel.
+    try:
+        pool_docs, nc = 20_000, 1000
+        ptoks = torch.randn(pool_docs * ld, d, generator=torch.Generator(device=dev).manual_seed(8), device=dev).bfloat16()
+        poff = (torch.arange(pool_docs + 1, dtype=torch.int32) * ld).to(dev)
+        cand = torch.randint(0, pool_docs, (nq, nc), generator=torch.Generator(device=dev).manual_seed(9), device=dev,
+                             dtype=torch.int32)
+        ms = timed(lambda: eng.maxsim(q, ptoks, poff, cand=cand), 5, warm=2)
+        nbytes = float(nq) * nc * ld * d * 2
+        out["maxsim_4b_per_query_candidates"] = {
+            "ms_per_batch": ms, "queries_per_s": nq / ms * 1e3,
+            "roofline": {"bound": "hbm", "achieved": nbytes / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": nbytes / ms / 1e6 / hbm_peak, "traffic": None, "peak_source": "measured"}}
+    except Exception as e:  # noqa: BLE001
+        out["maxsim_4b_per_query_candidates"] = {"error": str(e)}
     return out
 
 
