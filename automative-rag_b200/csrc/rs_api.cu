@@ -359,7 +359,7 @@ int rs_rerank_postprocess(rs_handle* h, const float* scores, const float* other,
   if (nq == 0 || top_k == 0) return RS_OK;
   if (!scores || !out_idx || !out_scores) return fail(h, RS_ERR_INVALID_ARG, "rs_rerank_postprocess: NULL buffer");
   if (nq < 0 || n < 1 || top_k < 0) return fail(h, RS_ERR_INVALID_ARG, "rs_rerank_postprocess: bad sizes");
-  if (n > 4096) return fail(h, RS_ERR_UNSUPPORTED, "rs_rerank_postprocess: n must be <= 4096 (got %d)", n);
+  if (n > 16384) return fail(h, RS_ERR_UNSUPPORTED, "rs_rerank_postprocess: n must be <= 16384 (got %d)", n);
   DeviceGuard guard(h->device);
   cudaError_t e = rs::launch_rerank_postprocess(scores, other, nq, n, w_a, w_b, top_k, out_idx, out_scores,
                                                 static_cast<cudaStream_t>(stream));

@@ -141,26 +141,12 @@ class B200ColBERTReranker:
         """(input index, final score) in reference order for one query's score vector(s)."""
         n = scores.numel()
         k = n if top_k is None else min(top_k, n)
-        if n <= 4096:
-            idx, out = self.engine.rerank_postprocess(
-                scores.reshape(1, n), None if other is None else other.reshape(1, n), k,
-                self.colbert_weight, self.bge_weight)
-            return list(zip(idx[0].tolist(), out[0].tolist()))
-        # candidate sets beyond the kernel's shared-memory sort: host ordering of the device scores
-        s = scores.tolist()
-        order = sorted(range(n), key=lambda i: s[i], reverse=True)
-        if other is None:
-            return [(i, s[i]) for i in order][:k]
-        o = other.tolist()
-
-        def mm(v):
-            lo, hi = min(v), max(v)
-            return [(x - lo) / (hi - lo) for x in v] if hi > lo else [1.0] * len(v)
-
-        a, b = mm([s[i] for i in order]), mm([o[i] for i in order])
-        comb = [self.colbert_weight * x + self.bge_weight * y for x, y in zip(a, b)]
-        ranked = sorted(zip(order, comb), key=lambda t: t[1], reverse=True)
-        return ranked[:k]
+        if n > 16384:
+            raise ValueError(f"rerank tail handles at most 16384 candidates per query on the device (got {n})")
+        idx, out = self.engine.rerank_postprocess(
+            scores.reshape(1, n), None if other is None else other.reshape(1, n), k,
+            self.colbert_weight, self.bge_weight)
+        return list(zip(idx[0].tolist(), out[0].tolist()))
 
     def _colbert_rerank(self, query: str, documents: List[Document]) -> List[Tuple[Document, float]]:
         """rerankers.py:351-385."""

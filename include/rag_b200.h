@@ -171,7 +171,7 @@ int rs_maxsim(rs_handle* h, const void* q, int32_t nq, int32_t lq, int32_t d, in
  *   if other != NULL: min-max normalise scores over the row (all-equal -> 1.0), min-max
  *   normalise `other` the same way, blend w_a * a + w_b * b, re-sort (stable);
  *   write the first top_k (index into the input row, final score).
- *   out_idx [nq, top_k] int32, out_scores [nq, top_k] fp32.   n <= 4096.
+ *   out_idx [nq, top_k] int32, out_scores [nq, top_k] fp32.   n <= 16384.
  */
 int rs_rerank_postprocess(rs_handle* h, const float* scores, const float* other, int32_t nq,
                           int32_t n, float w_a, float w_b, int32_t top_k, int32_t* out_idx,

@@ -116,3 +116,29 @@ def test_rerank_postprocess_kernel_matches_reference_golden(engine, name):
     idx, out = engine.rerank_postprocess(s, o, spec["top_k"] or s.shape[1])
     assert idx[0].tolist() == [i for i, _ in gold]
     np.testing.assert_allclose(out[0].cpu().numpy(), [v for _, v in gold], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("n,hybrid", [(1, False), (5000, False), (16384, True), (777, True)])
+def test_rerank_postprocess_large_and_tied_inputs(engine, n, hybrid):
+    """Stable order at sizes up to the device limit, with many exactly tied scores."""
+    rng = np.random.default_rng(n)
+    a = np.round(rng.standard_normal((2, n)).astype(np.float32), 1)      # heavy ties
+    b = np.round(rng.standard_normal((2, n)).astype(np.float32), 1) if hybrid else None
+    top_k = min(n, 50)
+    idx, out = engine.rerank_postprocess(torch.from_numpy(a).to(engine.device),
+                                         None if b is None else torch.from_numpy(b).to(engine.device), top_k)
+    for q in range(2):
+        want = omaxsim.hybrid_rerank(a[q].tolist(), None if b is None else b[q].tolist(), 0.8, 0.2, top_k)
+        got_idx = idx[q].cpu().tolist()
+        if not hybrid:
+            assert got_idx == [i for i, _ in want]        # exact: pure integer / ordering work
+        else:
+            # blended scores are fp32 on the device and float64 in Python: order may differ only inside fp32 ties
+            ws = np.array([s for _, s in want])
+            np.testing.assert_allclose(out[q].cpu().numpy(), ws, rtol=1e-5, atol=1e-6)
+            assert sorted(got_idx) == sorted(i for i, _ in want) or np.isclose(ws[-1], out[q, -1].item(), atol=1e-6)
+
+
+def test_rerank_postprocess_rejects_oversized_candidate_sets(engine):
+    with pytest.raises(ValueError):
+        engine.rerank_postprocess(torch.zeros(1, 20000, device=engine.device), None, 10)
