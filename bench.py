@@ -247,14 +247,12 @@ def run_b200(args):
 
     log(f"rank {rank}/{world}: corpus rows [{lo}, {hi}) resident, warm-up")
     # clocks are sampled every 20 ms from the warm-up on (same load as the timed steps): a sharded timed region
-    # can be shorter than one nvidia-smi sampling period
+    # can be shorter than one nvidia-smi sampling period.  Exactly W warm-up steps are run.
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.15)  # let nvidia-smi come up
-    est_step_s = nq * 3.0e-4 * (args.rows / N_ROWS) / world        # ~300 us per query per 1M rows per GPU
-    warm_steps = max(args.warmup, int(0.3 / max(est_step_s, 1e-4)) + 1)  # >= W steps and >= ~0.3 s of load
-    for _ in range(warm_steps):
+    for _ in range(args.warmup):
         step_device()
     barrier()
     log("timed region")
@@ -366,7 +364,7 @@ def run_b200(args):
             "dtype": "f16 in / f32 accumulate", "data": "synthetic",
             "config": {"workload": "config2", "rows": args.rows, "rows_per_gpu": rows_local, "dim": DIM, "k": k,
                        "mask_p": args.mask_p, "queries_per_step": nq, "parallelism": f"row-shard x{world}",
-                       "warmup_steps_run": warm_steps,
+
                        "l2": (f"inputs larger than L2: every query re-reads its {rows_local * DIM * 2 / 1e6:.0f} MB shard "
                               "(126 MB L2, loads carry an evict_first hint)")},
             "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": nq * DIM * 2, "d2h_bytes_per_step": nq * k * 12,
