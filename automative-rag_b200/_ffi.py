@@ -31,6 +31,7 @@ SIGNATURES = {
     "rs_launch_count": (_I64, [_P]),
     "rs_set_dense_impl": (C.c_int, [_P, C.c_int]),
     "rs_set_maxsim_impl": (C.c_int, [_P, C.c_int]),
+    "rs_set_scan_trace": (C.c_int, [_P, _P]),
     "rs_last_dense_impl": (C.c_int, [_P]),
     "rs_last_maxsim_impl": (C.c_int, [_P]),
     "rs_dense_topk": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _I32, _P, _I64, _I32, _I64, _P, _P, _P]),
@@ -140,6 +141,10 @@ class Engine:
 
     def set_maxsim_impl(self, impl: int) -> None:
         self._check(self._lib.rs_set_maxsim_impl(self._h, impl), "rs_set_maxsim_impl")
+
+    def set_scan_trace(self, trace: Optional[torch.Tensor]) -> None:
+        """Diagnostics: int64 device tensor [8, num_sms, 8] receiving per-CTA phase time stamps (None detaches)."""
+        self._check(self._lib.rs_set_scan_trace(self._h, trace.data_ptr() if trace is not None else None), "rs_set_scan_trace")
 
     @property
     def last_dense_impl(self) -> int:

@@ -61,6 +61,15 @@ __device__ __forceinline__ uint64_t policy_evict_normal_() {
   return pol;
 }
 
+// diagnostics: thread 0 stamps phase i of its CTA when a trace buffer is attached (rs_set_scan_trace)
+__device__ __forceinline__ void scan_trace(const ScanParams& p, int i) {
+  if (p.trace != nullptr && threadIdx.x == 0) {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[blockIdx.x * 8 + i] = t;
+  }
+}
+
 template <typename T, int NCH>
 __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -93,6 +102,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
   // griddepcontrol.wait below (before this grid publishes into its buffer) orders grid N+2 after
   // grid N, the previous user of the same buffer.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  scan_trace(p, 0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -102,6 +112,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
     fence_mbar_init();
   }
   __syncthreads();
+  scan_trace(p, 1);
 
   if (warp == kScanProducerWarp) {
     // ------------------------------------------------------------------ TMA producer warp
@@ -287,9 +298,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
     const int rounds_per_check = max(1, (p.buf_cap >> 1) / (NW * tile_rows));
 
     const bool two_slots = S == 2 * NW;  // this warp alternates between slots warp and warp + NW
+    scan_trace(p, 2);
     for (int r = 0;; ++r) {
       const int stage = warp + ((two_slots && (r & 1)) ? NW : 0);
       mbar_wait(&full_bar[stage], (uint32_t)((two_slots ? (r >> 1) : r) & 1));
+      if (r == 0) scan_trace(p, 3);
       const int sn = slot_n[stage];
       if (sn == kSlotEnd) {  // all consumer warps see END in the same round
         break;
@@ -336,7 +349,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
       }
       if ((r + 1) % rounds_per_check == 0) buf.maybe_compact();
     }
+    scan_trace(p, 4);
     buf.compact();  // final: keys[0..k) sorted descending (0 = empty)
+    scan_trace(p, 5);
 
     // ------------------------------------------------------------------ cross-CTA merge
     asm volatile("griddepcontrol.wait;" ::: "memory");  // previous grid fully done (no-op without PDL)
@@ -349,6 +364,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
       *s_flag = (ticket == gridDim.x - 1) ? 1 : 0;
     }
     named_bar_sync(kConsumerBar, consumer_threads);
+    scan_trace(p, 6);
     if (*s_flag) {
       __threadfence();
       // The buffer already holds this CTA's own top-k with the matching threshold; stream the
@@ -392,6 +408,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
         }
       }
       if (threadIdx.x == 0) *p.ticket = 0u;  // ready for the next launch on this stream
+      scan_trace(p, 7);
     }
   }
 }

@@ -25,6 +25,7 @@ struct ScanParams {
   int32_t consumers;       // consumer warps, filled by the launcher (stages is a multiple of it)
   int32_t buf_cap;         // filled by the launcher
   int32_t l2_policy;       // 0 evict_first (default), 1 normal, 2 evict_last
+  uint64_t* trace;         // diagnostics (rs_set_scan_trace): [grid][8] %globaltimer stamps, or null
 };
 int scan_tile_rows(int d);
 size_t scan_smem_bytes(int d, int k);

@@ -24,6 +24,7 @@ struct rs_handle {
   uint64_t* ws_keys = nullptr;  // 2 x [num_sms, 2048]: consecutive scans alternate (they may overlap under PDL)
   unsigned* ticket = nullptr;   // 2 counters, 128 bytes apart
   uint64_t scan_seq = 0;
+  uint64_t* scan_trace = nullptr;  // diagnostics: caller's device buffer [8][num_sms][8], see rs_set_scan_trace
   // *_host staging
   void* pinned = nullptr;      // mapped pinned memory: staged inputs, and results written by the kernel itself
   void* pinned_dev = nullptr;  // device alias of `pinned`
@@ -173,6 +174,11 @@ int rs_set_maxsim_impl(rs_handle* h, int impl) {
   h->maxsim_impl = impl;
   return RS_OK;
 }
+int rs_set_scan_trace(rs_handle* h, uint64_t* trace_dev) {
+  if (!h) return fail(h, RS_ERR_INVALID_ARG, "rs_set_scan_trace: null handle");
+  h->scan_trace = trace_dev;
+  return RS_OK;
+}
 int rs_last_dense_impl(const rs_handle* h) { return h ? h->last_dense_impl : 0; }
 int rs_last_maxsim_impl(const rs_handle* h) { return h ? h->last_maxsim_impl : 0; }
 
@@ -226,6 +232,7 @@ int rs_dense_topk(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_
     p.k = k;
     p.metric = metric;
     p.id_base = id_base;
+    if (h->scan_trace) p.trace = h->scan_trace + (h->scan_seq & 7) * (size_t)h->num_sms * 8;
     const int buf = (int)(h->scan_seq++ & 1);
     p.ws_keys = h->ws_keys + (size_t)buf * h->num_sms * kMaxK;
     p.ticket = h->ticket + buf * 32;

@@ -97,6 +97,13 @@ int64_t rs_launch_count(const rs_handle* h);
 /* Force a kernel family (RS_*_AUTO restores shape-based choice). */
 int rs_set_dense_impl(rs_handle* h, int impl);
 int rs_set_maxsim_impl(rs_handle* h, int impl);
+/*
+ * Diagnostics: attach (or, with NULL, detach) a device buffer of 8 x num_sms x 8 uint64 into which
+ * the single-query scan stamps %globaltimer at 8 points of every CTA's life (entry, barriers ready,
+ * query loaded, first tile landed, last tile consumed, local top-k sorted, list published, merge
+ * done); launch i writes block (i mod 8).  Used by scripts/scan_trace.py; off by default.
+ */
+int rs_set_scan_trace(rs_handle* h, uint64_t* trace_dev);
 /* Family used by the most recent rs_dense_topk / rs_maxsim call on this handle. */
 int rs_last_dense_impl(const rs_handle* h);
 int rs_last_maxsim_impl(const rs_handle* h);
