@@ -6,8 +6,9 @@
 // construction: 2*d bytes per passing row, ~2 flops per byte.
 //
 // Shape of the kernel (B200: 148 SMs, one persistent CTA per SM):
-//   * warp 13 is the TMA producer.  The CTA owns mask words b, b+grid, ... (one word = 32
-//     consecutive rows).  The producer turns passing rows into TILES of TILE_ROWS rows (4 rows =
+//   * warp 13 is the TMA producer.  It takes runs of 1..32 consecutive mask words (one word = 32
+//     consecutive rows) from an atomic counter, 32 at a time while plenty is left and fewer towards
+//     the end, so a CTA that starts late or streams slower takes less.  The producer turns passing rows into TILES of TILE_ROWS rows (4 rows =
 //     8 KB at d = 1024) in a shared-memory ring, up to 8 tiles per warp pass — lane l claims ring
 //     slot l of the pass, waits for it and issues its copies, so the mbarrier round trips of the
 //     pass overlap (a one-lane producer cost ~600 cycles per tile and capped the kernel at 5.7 TB/s):
@@ -53,6 +54,8 @@ constexpr int kConsumerBar = 1;   // named barrier id for the consumer threads
 constexpr int kRowQueue = 2048;   // pending passing rows (power of two >= 32 words x 32 rows + a tile)
 constexpr int kSlotContig = 0x100;  // slot_n flag: row ids are slot_rows[0] + lane (else slot_rows[lane])
 constexpr int kSlotEnd = -1;
+constexpr int kTournamentMaxK = 32;   // cross-CTA merge: tournament up to this k (~0.15 us per result), streaming compaction above
+constexpr int kTournamentLists = 5;   // lists per lane of the tournament warp (grid <= 160)
 constexpr int kDenseWordBits = 24;  // words with >= 24 of 32 rows passing are staged whole (<= 25% extra bytes)
 
 __device__ __forceinline__ uint64_t policy_evict_normal_() {
@@ -119,7 +122,30 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
     const uint64_t pol = p.l2_policy == 0 ? policy_evict_first() : (p.l2_policy == 1 ? policy_evict_normal_() : policy_evict_last());
     const uint32_t* mask = p.mask;
     const int64_t num_words = (p.n + 31) >> 5;
-    const int64_t my_words = (num_words > blockIdx.x) ? (num_words - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // Work is handed out through one atomic counter per launch, GUIDED: a grab takes up to 32
+    // consecutive mask words (one per lane, as many as a warp pass handles) while plenty of work is
+    // left and shrinks to remaining/grid words (>= unit_words) towards the end.  CTAs that start
+    // late (the SM that ran the previous query's merge) or sit on a slower path to HBM take fewer
+    // words, and the grid finishes within about one word's time of each other.
+    const int64_t wmin = p.unit_words, gmax = p.grab_max;
+    // The first first_words words of every CTA are fixed (CTA b starts at word b * first_words
+    // without a round trip to the counter); the counter hands out the words after grid * first_words.
+    const int64_t dyn_base = (int64_t)p.first_words * gridDim.x;
+    unsigned long long grab_pending = 0ull;
+    int64_t seen = 0;     // latest counter value this CTA has observed
+    int g_pending = 0;    // words requested by the outstanding grab
+    auto grab_issue = [&]() {  // lane 0 takes the next words; the result is read later (grab_result)
+      int64_t g = (num_words - seen) / (int64_t)gridDim.x;
+      g = g < wmin ? wmin : (g > gmax ? gmax : g);
+      g_pending = (int)g;
+      if (lane == 0) grab_pending = atomicAdd(p.unit_counter, (unsigned long long)g);
+    };
+    auto grab_result = [&](int64_t& start, int& count) {
+      start = dyn_base + (int64_t)__shfl_sync(0xFFFFFFFFu, grab_pending, 0);
+      seen = start + g_pending;
+      const int64_t left = num_words - start;
+      count = left <= 0 ? 0 : (left < g_pending ? (int)left : g_pending);
+    };
     const uint8_t* corpus = reinterpret_cast<const uint8_t*>(p.corpus);
     // Ring cursor, warp-uniform, kept incrementally (no 64-bit div/mod on the issue path):
     // the next tile goes to slot `slot` in ring pass `phase`; `posmod` = position % NW.
@@ -128,9 +154,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
     uint32_t head = 0, tail = 0;  // row queue (warp-uniform)
     const int batch_max = min(S, 8);  // tiles issued per warp pass, one per lane
 
-    auto word_bits = [&](int64_t wi) -> uint32_t {  // filter bits of this CTA's wi-th word
-      if (wi >= my_words) return 0u;
-      const int64_t gw = blockIdx.x + wi * gridDim.x;
+    auto word_bits = [&](int64_t gw) -> uint32_t {  // filter bits of global mask word gw
+      if (gw >= num_words) return 0u;
       const int64_t left = p.n - (gw << 5);
       const uint32_t in_range = left >= 32 ? 0xFFFFFFFFu : ((1u << (int)left) - 1u);
       return mask ? (__ldg(mask + gw) & in_range) : in_range;
@@ -213,12 +238,27 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
 
     const uint32_t all_bits = tile_rows == 32 ? 0xFFFFFFFFu : ((1u << tile_rows) - 1u);
     const int tiles_per_word = 32 / tile_rows;
-    uint32_t bits_cur = word_bits(lane);
-    for (int64_t wb = 0; wb < my_words; wb += 32) {
-      const uint32_t bits_nxt = word_bits(wb + 32 + lane);  // one batch ahead of its use
-      // ---- 32 words at once, one per lane
-      const uint32_t w = bits_cur;  // 0 beyond my_words
-      const uint32_t row0 = (uint32_t)((blockIdx.x + (wb + lane) * gridDim.x) << 5);
+    // Two grabs are in flight ahead of the words being issued: the next grab's filter words are
+    // loading and the grab after it is outstanding while the current words' tiles are issued.
+    int64_t w_cur, w_nxt;
+    int c_cur, c_nxt;
+    seen = dyn_base;
+    grab_issue();
+    if (p.first_words > 0) {
+      w_cur = (int64_t)blockIdx.x * p.first_words;
+      c_cur = p.first_words;
+    } else {
+      grab_result(w_cur, c_cur);
+      if (c_cur > 0) grab_issue();
+    }
+    uint32_t bits_cur = lane < c_cur ? word_bits(w_cur + lane) : 0u;
+    while (c_cur > 0) {
+      grab_result(w_nxt, c_nxt);
+      const uint32_t bits_nxt = lane < c_nxt ? word_bits(w_nxt + lane) : 0u;
+      if (c_nxt > 0) grab_issue();
+      // ---- up to 32 words at once, one per lane
+      const uint32_t w = bits_cur;  // 0 beyond the grab / the corpus
+      const uint32_t row0 = (uint32_t)((w_cur + lane) << 5);
       const bool dense = __popc(w) >= kDenseWordBits && (int64_t)row0 + 32 <= p.n;
       // sparse words: append their passing row ids to the queue (exclusive scan of the popcounts
       // gives every lane its offset; each lane then walks its own set bits)
@@ -263,6 +303,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
         }
       }
       bits_cur = bits_nxt;
+      w_cur = w_nxt;
+      c_cur = c_nxt;
     }
     if (tail != head) issue_gather(1, (int)(tail - head));
     while (posmod) issue_marker(min(NW - posmod, batch_max), 0);  // pad the last round
@@ -365,7 +407,74 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
     }
     named_bar_sync(kConsumerBar, consumer_threads);
     scan_trace(p, 6);
-    if (*s_flag) {
+    if (*s_flag && p.k <= kTournamentMaxK && gridDim.x <= 32 * kTournamentLists &&
+        (size_t)gridDim.x * p.k * sizeof(uint64_t) <= (size_t)S * tile_bytes) {
+      // ---- small k: tournament.  Every CTA's sorted list is copied into the (now idle) tile ring
+      // with one round of independent loads; then ONE warp pops the k winners: lane l holds the heads
+      // of lists l, l+32, ...; each step is a warp max (two REDUX) and one shared-memory load by the
+      // winning lane.  ~60 ns per result instead of a barrier-separated compaction per key.
+      __threadfence();
+      uint64_t* all = reinterpret_cast<uint64_t*>(stage_base);
+      const int total = (int)gridDim.x * p.k;
+      for (int i0 = threadIdx.x; i0 < total; i0 += consumer_threads * 4) {
+        uint64_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * consumer_threads;
+          v[u] = i < total ? __ldcg(p.ws_keys + i) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * consumer_threads;
+          if (i < total) all[i] = v[u];
+        }
+      }
+      named_bar_sync(kConsumerBar, consumer_threads);
+      if (warp == 0) {
+        uint64_t head[kTournamentLists];
+        int pos[kTournamentLists];
+        uint64_t best = 0ull;  // this lane's largest head; only the winning lane's changes per step
+#pragma unroll
+        for (int j = 0; j < kTournamentLists; ++j) {
+          const int list = lane + 32 * j;
+          pos[j] = list * p.k;
+          head[j] = list < (int)gridDim.x ? all[pos[j]] : 0ull;
+          best = head[j] > best ? head[j] : best;
+        }
+        for (int t = 0; t < p.k; ++t) {
+          // keys are unique (the row id is part of the key), so exactly one lane holds the maximum
+          const uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, (uint32_t)(best >> 32));
+          const uint32_t lo = __reduce_max_sync(0xFFFFFFFFu, (uint32_t)(best >> 32) == hi ? (uint32_t)best : 0u);
+          const uint64_t win = ((uint64_t)hi << 32) | lo;
+          if (win == 0ull) {  // every list exhausted: fewer than k rows passed the filter
+            for (int i = t + lane; i < p.k; i += 32) {
+              p.out_scores[i] = -INFINITY;
+              p.out_ids[i] = -1;
+            }
+            break;
+          }
+          if (best == win) {
+            p.out_scores[t] = key_score(win);
+            p.out_ids[t] = p.id_base + (int64_t)key_row(win);
+            best = 0ull;
+#pragma unroll
+            for (int j = 0; j < kTournamentLists; ++j) {
+              if (head[j] == win) {
+                const int list = lane + 32 * j;
+                ++pos[j];
+                head[j] = pos[j] < (list + 1) * p.k ? all[pos[j]] : 0ull;
+              }
+              best = head[j] > best ? head[j] : best;
+            }
+          }
+        }
+        if (lane == 0) {  // ready for the next launch that uses this workspace / this counter
+          *p.ticket = 0u;
+          *p.unit_counter = 0ull;
+        }
+      }
+      scan_trace(p, 7);
+    } else if (*s_flag) {
       __threadfence();
       // The buffer already holds this CTA's own top-k with the matching threshold; stream the
       // other CTAs' sorted lists through it.  Thread t walks list t (+lists_per_pass, ...); a list is
@@ -407,7 +516,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
           p.out_ids[i] = p.id_base + (int64_t)key_row(key);
         }
       }
-      if (threadIdx.x == 0) *p.ticket = 0u;  // ready for the next launch on this stream
+      if (threadIdx.x == 0) {  // ready for the next launch that uses this workspace / this counter
+        *p.ticket = 0u;
+        *p.unit_counter = 0ull;
+      }
       scan_trace(p, 7);
     }
   }
@@ -484,14 +596,32 @@ size_t scan_smem_bytes(int d, int k) {
   return (size_t)scan_stages(d, k) * tile_bytes + scan_fixed_smem(k);
 }
 
+// Smallest grab, in mask words: at least 64 KB of rows, so that the counter's round trip (~1 us)
+// stays hidden behind the ring (26 x 8 KB already issued ahead) also at the very end.
+static int scan_unit_words(int d) {
+  static const int forced = env_int("RS_SCAN_UNIT_WORDS", 0);
+  if (forced > 0) return forced > 32 ? 32 : forced;
+  const int64_t word_bytes = 32ll * d * 2;
+  const int64_t lo = (64 * 1024 + word_bytes - 1) / word_bytes;
+  return lo > 32 ? 32 : (int)lo;
+}
+
 cudaError_t launch_dense_scan(ScanParams p, int dtype, int num_sms, bool pdl, cudaStream_t stream) {
   p.tile_rows = scan_tile_rows(p.d);
   scan_ring(p.d, p.k, p.consumers, p.stages);
   p.buf_cap = TopKBuffer::capacity_for(p.k);
   static const int l2_policy = env_int("RS_SCAN_L2_POLICY", 0);
   p.l2_policy = l2_policy;
-  const int64_t num_words = (p.n + 31) / 32;  // a CTA owns whole mask words (32 rows)
-  int grid = (int)(num_words < (int64_t)num_sms ? (num_words > 0 ? num_words : 1) : num_sms);
+  const int64_t num_words = (p.n + 31) / 32;  // a mask word covers 32 rows
+  p.unit_words = scan_unit_words(p.d);
+  static const int grab_max = env_int("RS_SCAN_GRAB_MAX", 32);
+  p.grab_max = grab_max < p.unit_words ? p.unit_words : (grab_max > 32 ? 32 : grab_max);
+  const int64_t num_units = (num_words + p.unit_words - 1) / p.unit_words;
+  int grid = (int)(num_units < (int64_t)num_sms ? (num_units > 0 ? num_units : 1) : num_sms);
+  // static head start: about a quarter of each CTA's share, whole grabs only
+  int64_t first = num_words / ((int64_t)grid * 4);
+  first = first > p.grab_max ? p.grab_max : first;
+  p.first_words = first < p.unit_words ? 0 : (int32_t)first;
   const size_t smem = scan_smem_bytes(p.d, p.k);
   if (dtype == 0) return launch_scan_t<__half>(p, grid, smem, pdl, stream);
   return launch_scan_t<__nv_bfloat16>(p, grid, smem, pdl, stream);

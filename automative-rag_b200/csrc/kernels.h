@@ -25,6 +25,10 @@ struct ScanParams {
   int32_t consumers;       // consumer warps, filled by the launcher (stages is a multiple of it)
   int32_t buf_cap;         // filled by the launcher
   int32_t l2_policy;       // 0 evict_first (default), 1 normal, 2 evict_last
+  unsigned long long* unit_counter;  // next unclaimed mask word of this launch; 0 on entry, reset by the merging CTA
+  int32_t unit_words;      // smallest grab in mask words (32 rows each), filled by the launcher
+  int32_t grab_max;        // largest grab in mask words (<= 32), filled by the launcher
+  int32_t first_words;     // words per CTA handed out statically before the counter is used (0 = none)
   uint64_t* trace;         // diagnostics (rs_set_scan_trace): [grid][8] %globaltimer stamps, or null
 };
 int scan_tile_rows(int d);

@@ -24,6 +24,8 @@ struct rs_handle {
   uint64_t* ws_keys = nullptr;  // 2 x [num_sms, 2048]: consecutive scans alternate (they may overlap under PDL)
   unsigned* ticket = nullptr;   // 2 counters, 128 bytes apart
   uint64_t scan_seq = 0;
+  // scan work counters: launch i uses counter (i mod kScanCounters), which the launch itself leaves at zero
+  unsigned long long* unit_ctr = nullptr;
   uint64_t* scan_trace = nullptr;  // diagnostics: caller's device buffer [8][num_sms][8], see rs_set_scan_trace
   // *_host staging
   void* pinned = nullptr;      // mapped pinned memory: staged inputs, and results written by the kernel itself
@@ -45,6 +47,10 @@ struct rs_handle {
 namespace {
 
 constexpr int kMaxK = 2048;
+// A launch that has started but not completed keeps at least one CTA resident, and at most 148 SMs x 4 CTAs
+// (448 threads each) fit on the device, so launches i and i + 1024 are never in flight together: by the time a
+// counter is used again its previous launch has completed, i.e. its merging CTA has reset it.
+constexpr int kScanCounters = 1024;
 
 int fail(rs_handle* h, int code, const char* fmt, ...) {
   char buf[512];
@@ -136,6 +142,8 @@ int rs_create(int device, rs_handle** out) {
   if (e == cudaSuccess) e = cudaMalloc(&h->ws_keys, (size_t)2 * h->num_sms * kMaxK * sizeof(uint64_t));
   if (e == cudaSuccess) e = cudaMalloc(&h->ticket, 256);
   if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, 256);
+  if (e == cudaSuccess) e = cudaMalloc(&h->unit_ctr, kScanCounters * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(h->unit_ctr, 0, kScanCounters * sizeof(unsigned long long));
   if (e != cudaSuccess) {
     int rc = cuda_fail(nullptr, e, "rs_create: workspace allocation");
     rs_destroy(h);
@@ -153,6 +161,7 @@ int rs_destroy(rs_handle* h) {
   if (h->tc5) rs::tc5_destroy(h->tc5);
   if (h->ws_keys) cudaFree(h->ws_keys);
   if (h->ticket) cudaFree(h->ticket);
+  if (h->unit_ctr) cudaFree(h->unit_ctr);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->dev_stage) cudaFree(h->dev_stage);
   if (h->filt_dev) cudaFree(h->filt_dev);
@@ -238,6 +247,8 @@ int rs_dense_topk(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_
     p.ticket = h->ticket + buf * 32;
     p.out_scores = out_scores + (size_t)qi * k;
     p.out_ids = out_ids + (size_t)qi * k;
+    const int ctr = (int)((h->scan_seq - 1) & (kScanCounters - 1));
+    p.unit_counter = h->unit_ctr + ctr;
     cudaError_t e = rs::launch_dense_scan(p, dtype, h->num_sms, /*pdl=*/qi > 0, st);
     if (e != cudaSuccess) return cuda_fail(h, e, "dense_scan_kernel launch");
     h->launches += 1;
