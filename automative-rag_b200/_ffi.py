@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "librag_b200.so")
 RS_OK, RS_ERR_INVALID_ARG, RS_ERR_UNSUPPORTED, RS_ERR_CUDA, RS_ERR_NO_DEVICE, RS_ERR_NOMEM = 0, -1, -2, -3, -4, -5
 RS_F16, RS_BF16, RS_F32 = 0, 1, 2
 RS_METRIC_IP, RS_METRIC_COSINE = 0, 1
-RS_MAXSIM_AUTO, RS_MAXSIM_MMA, RS_MAXSIM_TCGEN05, RS_MAXSIM_SIMT = 0, 1, 2, 3
+RS_MAXSIM_AUTO, RS_MAXSIM_MMA, RS_MAXSIM_TCGEN05, RS_MAXSIM_SIMT, RS_MAXSIM_TCGEN05_CAND = 0, 1, 2, 3, 4
 RS_DENSE_AUTO, RS_DENSE_SCAN, RS_DENSE_TCGEN05 = 0, 1, 2
 
 # every symbol include/rag_b200.h declares: (restype, argtypes)

@@ -382,6 +382,7 @@ bool tc5_encode(const Tc5State* s, CUtensorMap* map, int dtype, int rank, const 
 }
 
 int tc5_num_sms(const Tc5State* s) { return s->num_sms; }
+bool tc5_has_encode(const Tc5State* s) { return s->encode != nullptr; }
 
 bool tc5_maxsim_supported(const Tc5State* s, int nq, int lq, int d, int nd, const int32_t* cand,
                           const int32_t* out_argmax) {

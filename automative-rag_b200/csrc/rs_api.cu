@@ -179,7 +179,7 @@ int rs_set_dense_impl(rs_handle* h, int impl) {
   return RS_OK;
 }
 int rs_set_maxsim_impl(rs_handle* h, int impl) {
-  if (!h || impl < RS_MAXSIM_AUTO || impl > RS_MAXSIM_SIMT) return fail(h, RS_ERR_INVALID_ARG, "rs_set_maxsim_impl: bad argument");
+  if (!h || impl < RS_MAXSIM_AUTO || impl > RS_MAXSIM_TCGEN05_CAND) return fail(h, RS_ERR_INVALID_ARG, "rs_set_maxsim_impl: bad argument");
   h->maxsim_impl = impl;
   return RS_OK;
 }
@@ -345,19 +345,35 @@ int rs_maxsim(rs_handle* h, const void* q, int32_t nq, int32_t lq, int32_t d, in
   if (h->maxsim_impl == RS_MAXSIM_SIMT) return fail(h, RS_ERR_UNSUPPORTED, "rs_maxsim: SIMT path takes fp32 inputs only");
   if (!aligned16(q) || !aligned16(doc_tokens)) return fail(h, RS_ERR_INVALID_ARG, "rs_maxsim: q and doc_tokens must be 16-byte aligned");
 
+  // Kernel family by shape: shared candidates with at least one full 128-row tile of query tokens -> the
+  // compute-bound tcgen05 kernel; per-query candidates (or too few query tokens) -> the document-streaming tcgen05
+  // kernel; argmax output or d outside {64, 128} -> the general mma.sync kernel.
   int impl = h->maxsim_impl;
   const bool tc5_ok = rs::tc5_maxsim_supported(h->tc5, nq, lq, d, nd, cand, out_argmax);
-  if (impl == RS_MAXSIM_AUTO) impl = tc5_ok ? RS_MAXSIM_TCGEN05 : RS_MAXSIM_MMA;
+  const bool cand_ok = rs::tc5_maxsim_cand_supported(h->tc5, nq, lq, d, nd, ndo, out_argmax);
+  if (impl == RS_MAXSIM_AUTO) impl = tc5_ok ? RS_MAXSIM_TCGEN05 : (cand_ok ? RS_MAXSIM_TCGEN05_CAND : RS_MAXSIM_MMA);
   if (impl == RS_MAXSIM_TCGEN05) {
     if (!tc5_ok)
       return fail(h, RS_ERR_UNSUPPORTED,
-                  "rs_maxsim: tcgen05 path needs shared candidates, no argmax, lq <= 128, d in {64,128,192,256}");
+                  "rs_maxsim: shared-candidate tcgen05 path needs cand == NULL, no argmax, lq <= 128, d in {64,128}, "
+                  "nq * lq_pad >= 128");
     int launched = 0;
     std::string err;
     int rc = rs::tc5_maxsim(h->tc5, p, dtype, st, &launched, &err);
     h->launches += launched;
     h->last_maxsim_impl = RS_MAXSIM_TCGEN05;
     if (rc != RS_OK) return fail(h, rc, "rs_maxsim(tcgen05): %s", err.c_str());
+    return RS_OK;
+  }
+  if (impl == RS_MAXSIM_TCGEN05_CAND) {
+    if (!cand_ok)
+      return fail(h, RS_ERR_UNSUPPORTED, "rs_maxsim: candidate tcgen05 path needs no argmax, lq <= 128, d in {64,128}");
+    int launched = 0;
+    std::string err;
+    int rc = rs::tc5_maxsim_cand(h->tc5, p, dtype, st, &launched, &err);
+    h->launches += launched;
+    h->last_maxsim_impl = RS_MAXSIM_TCGEN05_CAND;
+    if (rc != RS_OK) return fail(h, rc, "rs_maxsim(tcgen05 candidates): %s", err.c_str());
     return RS_OK;
   }
   if ((d % 16) != 0) return fail(h, RS_ERR_UNSUPPORTED, "rs_maxsim: d must be a multiple of 16 for fp16/bf16 (got %d)", d);

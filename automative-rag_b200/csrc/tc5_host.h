@@ -1,6 +1,7 @@
 // tc5_host.h — host interface of the tcgen05/TMEM/TMA kernels (maxsim_tc5.cu, dense_tc5.cu).
 // Owns the cuTensorMapEncodeTiled entry point and per-handle scratch for those kernels.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -18,6 +19,17 @@ void tc5_destroy(Tc5State* s);
 bool tc5_maxsim_supported(const Tc5State* s, int nq, int lq, int d, int nd, const int32_t* cand,
                           const int32_t* out_argmax);
 int tc5_maxsim(Tc5State* s, const MaxSimParams& p, int dtype, cudaStream_t stream, int* launched, std::string* err);
+
+// Per-query-candidate MaxSim (reference rerank shape, rerankers.py:351-385); also serves shared candidates when
+// there are too few query tokens for the kernel above (cand == null: candidate j of every query is document j).
+bool tc5_maxsim_cand_supported(const Tc5State* s, int nq, int lq, int d, int nd, int nc, const int32_t* out_argmax);
+int tc5_maxsim_cand(Tc5State* s, const MaxSimParams& p, int dtype, cudaStream_t stream, int* launched, std::string* err);
+
+// shared helpers (defined in maxsim_tc5.cu)
+bool tc5_has_encode(const Tc5State* s);
+int tc5_num_sms(const Tc5State* s);
+bool tc5_encode(const Tc5State* s, CUtensorMap* map, int dtype, int rank, const void* base, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, std::string* err);
 
 // Batched dense top-k (GEMM + fused per-row top-k).
 bool tc5_dense_supported(const Tc5State* s, int64_t n, int d, int nq, int k, const uint32_t* mask,

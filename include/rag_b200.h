@@ -76,7 +76,7 @@ enum {
 };
 
 /* which MaxSim kernel family to use (RS_MAXSIM_AUTO picks by shape) */
-enum { RS_MAXSIM_AUTO = 0, RS_MAXSIM_MMA = 1, RS_MAXSIM_TCGEN05 = 2, RS_MAXSIM_SIMT = 3 };
+enum { RS_MAXSIM_AUTO = 0, RS_MAXSIM_MMA = 1, RS_MAXSIM_TCGEN05 = 2, RS_MAXSIM_SIMT = 3, RS_MAXSIM_TCGEN05_CAND = 4 };
 
 /* which dense kernel family to use (RS_DENSE_AUTO picks by nq) */
 enum { RS_DENSE_AUTO = 0, RS_DENSE_SCAN = 1, RS_DENSE_TCGEN05 = 2 };

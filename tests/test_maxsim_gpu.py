@@ -94,7 +94,9 @@ def test_auto_dispatch_picks_tcgen05_for_shared_candidates(engine):
     toks, off = pack_documents(docs, engine.device, torch.bfloat16)
     engine.maxsim(q.to(engine.device), toks, off)
     assert engine.last_maxsim_impl == _ffi.RS_MAXSIM_TCGEN05
-    engine.maxsim(q[:1].to(engine.device), toks, off)  # a single query: general mma.sync kernel
+    engine.maxsim(q[:1].to(engine.device), toks, off)  # a single query: the document-streaming tcgen05 kernel
+    assert engine.last_maxsim_impl == _ffi.RS_MAXSIM_TCGEN05_CAND
+    engine.maxsim(q[:1].to(engine.device), toks, off, want_argmax=True)  # argmax: general mma.sync kernel
     assert engine.last_maxsim_impl == _ffi.RS_MAXSIM_MMA
 
 
@@ -105,10 +107,97 @@ def test_candidate_lists_mma_path(engine, dtype):
     toks, off = pack_documents(docs, engine.device, dtype)
     rng = np.random.default_rng(0)
     cand = np.stack([rng.permutation(len(docs))[:5] for _ in range(nq)]).astype(np.int32)
-    got = engine.maxsim(q.to(engine.device), toks, off, cand=torch.from_numpy(cand).to(engine.device))
+    engine.set_maxsim_impl(_ffi.RS_MAXSIM_MMA)
+    try:
+        got = engine.maxsim(q.to(engine.device), toks, off, cand=torch.from_numpy(cand).to(engine.device))
+    finally:
+        engine.set_maxsim_impl(_ffi.RS_MAXSIM_AUTO)
     assert engine.last_maxsim_impl == _ffi.RS_MAXSIM_MMA
     want = omaxsim.maxsim_scores_packed(q, None, torch.cat(docs), off.cpu().numpy(), cand)
     assert_scores_close(got.cpu().numpy(), want, rtol=RTOL_16BIT, atol=1e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("nq,lq,d,lens,nc", [
+    (6, 32, 128, [50, 120, 300, 7, 64, 200, 33, 90], 5),          # ragged documents, 1..3 chunks each
+    (1, 32, 128, [180] * 100, 0),                                  # BASELINE config 1 shape: one query, shared docs
+    (3, 32, 128, [1, 2, 31, 32, 33, 127, 128, 129, 255, 256, 257, 511, 513, 700], 9),  # chunk-edge lengths
+    (40, 32, 64, [180] * 30, 30),                                  # d = 64; more pairs than SMs, many query switches
+    (5, 20, 128, [64, 100, 300, 17], 3),                           # lq < 32: zero-padded query rows
+    (4, 45, 128, [90] * 12, 7),                                    # lq in (32, 64]: two epilogue warps
+    (3, 70, 64, [50, 60, 70, 300], 4),                             # lq in (64, 96]: three
+    (2, 128, 128, [140, 260, 20], 3),                              # lq = 128: four
+    (300, 32, 128, [40] * 8, 2),                                   # a query switch every other pair
+])
+def test_candidate_tcgen05_path_matches_oracle(engine, nq, lq, d, lens, nc, dtype):
+    """Per-query candidate lists (and shared lists with few queries, nc == 0) through the document-streaming
+    tcgen05 kernel vs the CPU oracle on the same rounded inputs; default and explicit token weights."""
+    q, docs = _batch_case(nq * 10 + lq, nq, lq, d, lens, dtype)
+    toks, off = pack_documents(docs, engine.device, dtype)
+    rng = np.random.default_rng(nq)
+    cand = None
+    if nc:
+        cand = np.stack([rng.permutation(len(docs))[:nc] if nc <= len(docs) else rng.integers(0, len(docs), nc)
+                         for _ in range(nq)]).astype(np.int32)
+    g = torch.Generator().manual_seed(5)
+    w = torch.rand(nq, lq, generator=g)
+    w[:, 0] = 0
+    for weight in (None, w):
+        engine.set_maxsim_impl(_ffi.RS_MAXSIM_TCGEN05_CAND)
+        try:
+            got = engine.maxsim(q.to(engine.device), toks, off,
+                                q_weight=None if weight is None else weight.to(engine.device),
+                                cand=None if cand is None else torch.from_numpy(cand).to(engine.device))
+        finally:
+            engine.set_maxsim_impl(_ffi.RS_MAXSIM_AUTO)
+        assert engine.last_maxsim_impl == _ffi.RS_MAXSIM_TCGEN05_CAND
+        want = omaxsim.maxsim_scores_packed(q, None if weight is None else weight, torch.cat(docs),
+                                            off.cpu().numpy(), cand)
+        assert_scores_close(got.cpu().numpy(), want, rtol=RTOL_16BIT, atol=1e-3, what="tcgen05 candidate maxsim")
+
+
+def test_candidate_tcgen05_empty_documents_and_bad_indices(engine):
+    """C-ABI edge: a zero-token document (the Python layer refuses those, as torch.max does in the reference) and a
+    candidate index outside the collection both score -inf; their neighbours are unaffected."""
+    dtype, d, lq = torch.bfloat16, 128, 32
+    q, docs = _batch_case(3, 2, lq, d, [300, 45, 128], dtype)
+    dev = engine.device
+    toks = torch.cat(docs).to(dev)
+    off = torch.tensor([0, 300, 300, 345, 345, 473], dtype=torch.int32, device=dev)   # docs 1 and 3 are empty
+    cand = torch.tensor([[0, 1, 2, 3, 4, 7], [4, -1, 3, 2, 0, 1]], dtype=torch.int32, device=dev)
+    engine.set_maxsim_impl(_ffi.RS_MAXSIM_TCGEN05_CAND)
+    try:
+        got = engine.maxsim(q.to(dev), toks, off, cand=cand).cpu().numpy()
+    finally:
+        engine.set_maxsim_impl(_ffi.RS_MAXSIM_AUTO)
+    real = {0: 0, 2: 1, 4: 2}
+    want = omaxsim.maxsim_scores_packed(q, None, torch.cat(docs), np.array([0, 300, 345, 473]))
+    for qi in range(2):
+        for c, j in enumerate(cand[qi].tolist()):
+            if j in real:
+                assert abs(got[qi, c] - want[qi, real[j]]) <= RTOL_16BIT * abs(want[qi, real[j]]) + 1e-3
+            else:
+                assert got[qi, c] == -np.inf
+
+
+def test_candidate_tcgen05_equals_mma_at_config4b_scale(engine):
+    """BASELINE config 4b shape scaled to 64 queries x 1000 own candidates out of a 4096-document pool (300 tokens,
+    bf16): the tcgen05 candidate kernel and the mma.sync kernel agree on every (query, candidate) pair."""
+    nq, lq, d, pool, ld, nc = 64, 32, 128, 4096, 300, 1000
+    dev = engine.device
+    g = torch.Generator(device=dev).manual_seed(8)
+    q = torch.randn(nq, lq, d, generator=g, device=dev).to(torch.bfloat16)
+    toks = torch.randn(pool * ld, d, generator=g, device=dev).to(torch.bfloat16)
+    off = (torch.arange(pool + 1, device=dev) * ld).to(torch.int32)
+    cand = torch.stack([torch.randperm(pool, generator=g, device=dev)[:nc] for _ in range(nq)]).to(torch.int32)
+    out = {}
+    for impl in (_ffi.RS_MAXSIM_TCGEN05_CAND, _ffi.RS_MAXSIM_MMA):
+        engine.set_maxsim_impl(impl)
+        try:
+            out[impl] = engine.maxsim(q, toks, off, cand=cand).cpu().numpy()
+        finally:
+            engine.set_maxsim_impl(_ffi.RS_MAXSIM_AUTO)
+    assert_scores_close(out[_ffi.RS_MAXSIM_TCGEN05_CAND], out[_ffi.RS_MAXSIM_MMA], rtol=RTOL_16BIT, atol=1e-3)
 
 
 def test_weights_reproduce_all_three_conventions(engine):
