@@ -334,8 +334,8 @@ def run_b200(args):
     avg_launch_ms = elapsed_ms / scan_launches  # launches are back to back on one stream
     achieved = alg_bytes / (avg_launch_ms * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this exact workload from the committed
-    # `ncu --set full` capture (profiles/r01_dense_scan_v3_ncu.txt): 2.048237 GB + 4.47 MB; null for other shapes
-    traffic = 2_052_708_808 if (world == 1 and args.rows == N_ROWS and k == TOPK and args.mask_p >= 1.0) else None
+    # `ncu --set full` capture (profiles/r01_dense_scan_v4_ncu.txt): 2.048201 GB + 3.71 MB; null for other shapes
+    traffic = 2_051_912_488 if (world == 1 and args.rows == N_ROWS and k == TOPK and args.mask_p >= 1.0) else None
     roofline = {"bound": "hbm", "kernel": "dense_scan_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": avg_launch_ms * 1e3}
@@ -494,7 +494,8 @@ def extra_measurements(eng, corpus, queries, dev, hbm_peak, peaks):
             eng.set_maxsim_impl(_ffi.RS_MAXSIM_AUTO)
     # BASELINE config 4b: per-query candidate lists (the retrieve-then-rerank shape): 256 queries, each with its
     # own 1000 documents drawn from a 20000-document pool (1.5 GB of bf16 tokens, 12x the L2) -> HBM-bound:
-    # 256 * 1000 * 300 * 128 * 2 B = 19.66 GB of token reads per batch.  Runs on the general mma.sync kernel.
+    # 256 * 1000 * 300 * 128 * 2 B = 19.66 GB of token reads per batch.  AUTO picks the document-streaming tcgen05
+    # kernel (maxsim_cand_tc5.cu); traffic = dram bytes of one launch from profiles/r01_maxsim_cand_v1_ncu.txt.
     try:
         pool_docs, nc = 20_000, 1000
         ptoks = torch.randn(pool_docs * ld, d, generator=torch.Generator(device=dev).manual_seed(8), device=dev).bfloat16()
@@ -506,7 +507,8 @@ def extra_measurements(eng, corpus, queries, dev, hbm_peak, peaks):
         out["maxsim_4b_per_query_candidates"] = {
             "ms_per_batch": ms, "queries_per_s": nq / ms * 1e3,
             "roofline": {"bound": "hbm", "achieved": nbytes / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": nbytes / ms / 1e6 / hbm_peak, "traffic": None, "peak_source": "measured"}}
+                         "frac": nbytes / ms / 1e6 / hbm_peak, "traffic": 19_725_812_248, "peak_source": "measured"},
+            "impl": {_ffi.RS_MAXSIM_MMA: "mma.sync", _ffi.RS_MAXSIM_TCGEN05_CAND: "tcgen05_cand"}.get(eng.last_maxsim_impl, "?")}
     except Exception as e:  # noqa: BLE001
         out["maxsim_4b_per_query_candidates"] = {"error": str(e)}
     return out

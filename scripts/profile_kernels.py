@@ -3,6 +3,7 @@
     python scripts/profile_kernels.py scan      # dense_scan_kernel, 1M x 1024 fp16, top-10
     python scripts/profile_kernels.py maxsim    # maxsim_tc5_kernel, config 4a
     python scripts/profile_kernels.py maxsim_mma
+    python scripts/profile_kernels.py maxsim_cand # maxsim_cand_tc5_kernel, config 4b
     python scripts/profile_kernels.py dense_batch
 """
 import os
@@ -36,6 +37,16 @@ elif what in ("maxsim", "maxsim_mma"):
     eng.set_maxsim_impl(_ffi.RS_MAXSIM_TCGEN05 if what == "maxsim" else _ffi.RS_MAXSIM_MMA)
     for _ in range(iters):
         eng.maxsim(q, toks, off)
+elif what == "maxsim_cand":
+    nq, lq, d, pool, ld, nc = 256, 32, 128, 20_000, 300, 1000
+    g = torch.Generator(device=dev).manual_seed(8)
+    q = torch.randn(nq, lq, d, generator=g, device=dev).bfloat16()
+    toks = torch.randn(pool * ld, d, generator=g, device=dev).bfloat16()
+    off = (torch.arange(pool + 1, dtype=torch.int32) * ld).to(dev)
+    cand = torch.randint(0, pool, (nq, nc), generator=g, device=dev, dtype=torch.int32)
+    eng.set_maxsim_impl(_ffi.RS_MAXSIM_TCGEN05_CAND)
+    for _ in range(iters):
+        eng.maxsim(q, toks, off, cand=cand)
 elif what == "dense_batch":
     n, d, nq, k = 2_000_000, 1024, 1024, 100
     g = torch.Generator(device=dev).manual_seed(4)
