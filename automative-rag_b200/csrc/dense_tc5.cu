@@ -24,6 +24,8 @@
 //   * each CTA writes its per-query top-k lists; rs_topk_merge (one more small launch) merges the
 //     ranges.  Result order and tie rule are those of the scan: (score desc, id asc).
 #include <cuda.h>
+
+#include <cstdlib>
 #include <math_constants.h>
 
 #include "tc5.cuh"
@@ -58,6 +60,8 @@ struct DenseTcParams {
   int64_t n, id_base;
   int32_t nq, d, k, metric;
   int32_t num_ranges, tiles_total;
+  uint32_t* gthr;           // [num_ranges, nq] orderable score of each range's gm-th best row so far (0 = none yet)
+  int32_t gm;               // ceil(k / num_ranges) in 1..4, or 0 = no cross-CTA threshold
 };
 
 // warp-level bitonic sort of n (power of two, 64..512) u64 keys in shared memory, descending
@@ -189,7 +193,19 @@ __global__ void __launch_bounds__(kDtThreads, 1)
         q_scale = ss > 0.f ? rsqrtf(ss) : 0.f;
         if (ss > 0.f) q_scale = q_scale * (1.5f - 0.5f * ss * q_scale * q_scale);
       }
-      float thr = -CUDART_INF_F;  // k-th best score of this query so far (strict > keeps the lower id on ties)
+      // A row enters the candidate buffer when its score beats `thr` = max of two lower bounds on the final
+      // k-th best score of the query:
+      //   thr_local  the k-th best of THIS range so far (strict >: a later row of equal score has the higher id);
+      //   thr_cross  every range publishes its gm-th best score, gm = ceil(k / ranges); gm rows in each of the
+      //              ranges score at least the minimum T of those values, i.e. >= k rows overall, so nothing below
+      //              T can be in the answer (rows equal to T stay in: thr_cross is the float just below T).
+      // A range sees only 1/ranges of the corpus, so thr_local alone lets ~k/rows_seen of the rows through;
+      // T behaves like the k-th best of everything all ranges have seen and cuts that by an order of magnitude.
+      float thr_local = -CUDART_INF_F, thr_cross = -CUDART_INF_F, thr = -CUDART_INF_F;
+      float tm0 = -CUDART_INF_F, tm1 = -CUDART_INF_F, tm2 = -CUDART_INF_F, tm3 = -CUDART_INF_F;  // best 4 scores seen
+      const int gm = p.gm;
+      uint32_t* my_gthr = p.gthr + (size_t)range * p.nq + (valid ? query : 0);
+      const int cross_every = max(1, p.num_ranges / 32);  // tiles between refreshes of thr_cross
       int cnt = 0;
       const int k = p.k;
 
@@ -208,7 +224,10 @@ __global__ void __launch_bounds__(kDtThreads, 1)
         __syncwarp();
         if (lane == L) {
           cnt = kept;
-          if (kept == k) thr = key_score(kth);
+          if (kept == k) {
+            thr_local = key_score(kth);
+            thr = fmaxf(thr_local, thr_cross);
+          }
         }
       };
 
@@ -241,13 +260,28 @@ __global__ void __launch_bounds__(kDtThreads, 1)
             uint32_t bits = (p.n - r0 >= 32) ? 0xFFFFFFFFu : ((1u << (int)(p.n - r0)) - 1u);
             if (p.mask) bits &= __ldg(p.mask + (r0 >> 5));
             if (valid && m > thr) {
+              float cbest = -CUDART_INF_F;
 #pragma unroll
               for (int c = 0; c < 32; ++c) {
                 const float s = __uint_as_float(v[c]);
                 if (s > thr && ((bits >> c) & 1u)) {
                   __stcg(my_cand + cnt, make_key(s, (uint32_t)(r0 + c)));
                   ++cnt;
+                  cbest = fmaxf(cbest, s);
                 }
+              }
+              // Keep the best four scores sorted and publish the gm-th when it moves.  One insertion per chunk
+              // (its best appended row) keeps this out of the unrolled loop — 32 inlined copies pushed the kernel
+              // out of the instruction cache; a second top-gm row inside the same 32 rows only makes the bound
+              // looser, never wrong.
+              if (gm > 0 && cbest > tm3) {
+                const float before = gm == 1 ? tm0 : (gm == 2 ? tm1 : (gm == 3 ? tm2 : tm3));
+                tm3 = cbest;
+                if (tm3 > tm2) { const float x = tm2; tm2 = tm3; tm3 = x; }
+                if (tm2 > tm1) { const float x = tm1; tm1 = tm2; tm2 = x; }
+                if (tm1 > tm0) { const float x = tm0; tm0 = tm1; tm1 = x; }
+                const float after = gm == 1 ? tm0 : (gm == 2 ? tm1 : (gm == 3 ? tm2 : tm3));
+                if (after > before) __stcg(my_gthr, f32_orderable(after));
               }
             }
           }
@@ -277,6 +311,16 @@ __global__ void __launch_bounds__(kDtThreads, 1)
           const int L = __ffs(need) - 1;
           need &= need - 1;
           compact_lane(L);
+        }
+        // refresh the cross-range bound (also off the critical path; stale values are only lower, never wrong)
+        if (gm > 0 && valid && (t % cross_every) == cross_every - 1) {
+          uint32_t lo = 0xFFFFFFFFu;
+          const uint32_t* g = p.gthr + query;
+          for (int c = 0; c < p.num_ranges; ++c) lo = min(lo, __ldcg(g + (size_t)c * p.nq));
+          if (lo > 1u) {  // every range has published: the float just below T
+            thr_cross = orderable_f32(lo - 1u);
+            thr = fmaxf(thr_local, thr_cross);
+          }
         }
       }
       // ---- final: every query's buffer sorted, best k written as (score, id) lists of this range
@@ -356,8 +400,9 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
   }
   const size_t cand_bytes = (size_t)ranges * mgroups * (kDtMT * 128) * kDtCap * sizeof(uint64_t);
   const size_t ls_bytes = ((size_t)ranges * nq * k * sizeof(float) + 255) / 256 * 256;
-  const size_t li_bytes = (size_t)ranges * nq * k * sizeof(int64_t);
-  uint8_t* ws = static_cast<uint8_t*>(tc5_dense_scratch(s, cand_bytes + ls_bytes + li_bytes));
+  const size_t li_bytes = ((size_t)ranges * nq * k * sizeof(int64_t) + 255) / 256 * 256;
+  const size_t gt_bytes = (size_t)ranges * nq * sizeof(uint32_t);
+  uint8_t* ws = static_cast<uint8_t*>(tc5_dense_scratch(s, cand_bytes + ls_bytes + li_bytes + gt_bytes));
   if (!ws) {
     *err = "out of device memory for the candidate buffers";
     return -5;
@@ -377,6 +422,17 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
   kp.metric = metric;
   kp.num_ranges = ranges;
   kp.tiles_total = tiles_total;
+  kp.gthr = reinterpret_cast<uint32_t*>(ws + cand_bytes + ls_bytes + li_bytes);
+  static const int cross_off = getenv("RS_DENSE_NO_CROSS_THR") ? 1 : 0;  // A/B switch for scripts/batch_bench.py
+  const int gm = (k + ranges - 1) / ranges;
+  kp.gm = (ranges > 1 && gm <= 4 && !cross_off) ? gm : 0;
+  if (kp.gm > 0) {
+    cudaError_t me = cudaMemsetAsync(kp.gthr, 0, gt_bytes, stream);
+    if (me != cudaSuccess) {
+      *err = cudaGetErrorString(me);
+      return -3;
+    }
+  }
   const size_t smem = 1024 + (size_t)kDtStages * kDtStageBytes + 8 * kDtCap * sizeof(uint64_t) + 256;
   dim3 grid(ranges, mgroups);
   cudaError_t e;
