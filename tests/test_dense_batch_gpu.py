@@ -83,6 +83,52 @@ def test_batched_exact_ties_ordered_by_id(engine):
         assert i[j].tolist() == dup[:k]
 
 
+def test_batched_all_rows_equal_keeps_lowest_ids(engine):
+    """Every row scores the same: the cross-range bound equals that score, rows EQUAL to it must survive, and the
+    (score desc, id asc) order leaves exactly ids 0..k-1."""
+    n, d, nq, k = 40_000, 128, 64, 100
+    c, q = _case(12, n, d, nq, torch.bfloat16)
+    c[:] = c[0].clone()
+    s, i = _run(engine, c, q, k, _ffi.RS_DENSE_TCGEN05)
+    for j in range(nq):
+        assert i[j].tolist() == list(range(k))
+        assert (s[j] == s[j][0]).all()
+
+
+@pytest.mark.parametrize("order", ["ascending", "descending", "one_range_holds_all"])
+def test_batched_adversarial_row_orders(engine, order):
+    """Row orders that stress the running thresholds: scores rising with the row id (every row beats the local
+    bound), falling (bounds tight from the first tile), and all winners inside one range (the other ranges publish
+    low bounds, which must not cut anything)."""
+    n, d, nq, k = 60_000, 128, 40, 100
+    g = torch.Generator().manual_seed(13)
+    base = torch.randn(d, generator=g)
+    base = base / base.norm()
+    noise = torch.randn(n, d, generator=g) * 0.05
+    if order == "one_range_holds_all":
+        w = torch.full((n,), 0.1)
+        w[41_000:41_300] = torch.linspace(0.5, 1.0, 300)
+    else:
+        w = torch.linspace(0.1, 1.0, n) if order == "ascending" else torch.linspace(1.0, 0.1, n)
+    c = (w[:, None] * base[None, :] + noise).to(torch.bfloat16)
+    q = (base[None, :] + 0.01 * torch.randn(nq, d, generator=g)).to(torch.bfloat16)
+    s, i = _run(engine, c, q, k, _ffi.RS_DENSE_TCGEN05, metric=_ffi.RS_METRIC_IP)
+    _check_all(s, i, c, q, k, metric=_ffi.RS_METRIC_IP)
+
+
+def test_batched_masked_out_ranges(engine):
+    """Whole ranges filtered out: they never publish a bound, so no cross-range cut may happen — and the result is
+    still the exact top-k of the passing rows."""
+    n, d, nq, k = 50_000, 128, 48, 64
+    c, q = _case(14, n, d, nq, torch.float16)
+    bits = np.zeros(n, bool)
+    bits[30_000:30_500] = True
+    bits[49_990:] = True
+    mask = torch.from_numpy(odense.pack_mask(bits).view(np.int32).copy()).to(engine.device)
+    s, i = _run(engine, c, q, k, _ffi.RS_DENSE_TCGEN05, mask=mask)
+    _check_all(s, i, c, q, k, bits)
+
+
 def test_batched_agrees_with_scan_and_auto_dispatch(engine):
     n, d, nq, k = 50_000, 1024, 128, 100
     c, q = _case(11, n, d, nq, torch.bfloat16)
