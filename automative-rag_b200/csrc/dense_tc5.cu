@@ -38,11 +38,14 @@ bool tc5_encode(const Tc5State* s, CUtensorMap* map, int dtype, int rank, const 
 void* tc5_dense_scratch(Tc5State* s, size_t bytes);
 int tc5_num_sms(const Tc5State* s);
 
-constexpr int kDtThreads = 384;
+constexpr int kDtThreads = 384;   // single-CTA tiles: warps 0 TMA, 1 MMA, 2 TMEM, 4-7 / 8-11 epilogue sets
+constexpr int kDtThreadsPair = 256;  // CTA pairs: one epilogue set per CTA
 constexpr int kDtBN = 256;        // corpus rows per tile (UMMA N)
 constexpr int kDtBK = 64;         // K elements per stage (one 128-byte swizzle row)
-constexpr int kDtMT = 2;          // 128-query UMMA tiles per CTA
+constexpr int kDtMT = 2;          // 128-query UMMA tiles per CTA (single-CTA tiles) / CTAs per pair
 constexpr int kDtStages = 3;
+constexpr int kDtStagesPair = 6;  // a pair's stage is half the size: 128 query rows + 128 corpus rows per CTA
+constexpr int kDtMaxGm = 8;       // best scores tracked per (range, query) for the cross-range bound
 constexpr int kDtCap = 512;       // candidate buffer entries per (CTA, query): room for a whole tile (256 rows) of
                                   // appends on top of kDtCompactAt, so compaction can wait for the end of the tile
 constexpr int kDtCompactAt = 192; // compact a query's buffer once it holds more than this (keeps the sort at 256 keys)
@@ -61,7 +64,7 @@ struct DenseTcParams {
   int32_t nq, d, k, metric;
   int32_t num_ranges, tiles_total;
   uint32_t* gthr;           // [num_ranges, nq] orderable score of each range's gm-th best row so far (0 = none yet)
-  int32_t gm;               // ceil(k / num_ranges) in 1..4, or 0 = no cross-CTA threshold
+  int32_t gm;               // ceil(k / num_ranges) in 1..kDtMaxGm, or 0 = no cross-CTA threshold
 };
 
 // warp-level bitonic sort of n (power of two, 64..512) u64 keys in shared memory, descending
@@ -80,107 +83,161 @@ __device__ __forceinline__ void warp_sort_desc(uint64_t* keys, int n, int lane) 
   __syncwarp();
 }
 
-template <bool BF16>
+// PAIR = false: one CTA per (range, 256-query group), two 128-query UMMA tiles, both accumulators fill TMEM, so the
+//   epilogue and the MMAs of consecutive tiles alternate.
+// PAIR = true: a CTA PAIR (2-wide cluster = the two SMs of a TPC) per (range, 256-query group) runs ONE
+//   tcgen05.mma.cta_group::2 of M = 256: each CTA stages its 128 queries and HALF of the 256 corpus rows (the tensor
+//   cores read the other half from the peer's shared memory), and holds its 128 x 256 accumulator in its own TMEM —
+//   256 columns, so TMEM takes TWO accumulators and the epilogue of tile t overlaps the MMAs of tile t+1 at the same
+//   operand bytes per flop.  The leader (cluster rank 0) issues the MMAs; TMA loads of both CTAs count on the leader's
+//   barrier; tcgen05.commit multicasts "stage free" / "accumulator ready" to both; the peer's epilogue hands
+//   accumulators back with a remote mbarrier arrive.
+template <bool BF16, bool PAIR>
 __global__ void __launch_bounds__(kDtThreads, 1)
     dense_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
                      const DenseTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const int range = blockIdx.x, mgroup = blockIdx.y;
+  constexpr int kStages = PAIR ? kDtStagesPair : kDtStages;
+  constexpr int kMT = PAIR ? 1 : kDtMT;                       // 128-query tiles staged by this CTA
+  constexpr uint32_t kBRows = PAIR ? kDtBN / 2 : kDtBN;       // corpus rows staged by this CTA
+  constexpr uint32_t kBBytes = kBRows * 128;
+  constexpr uint32_t kStageBytes = kMT * kDtABytes + kBBytes;
+  constexpr int kAccBufs = PAIR ? 2 : 1;                      // accumulator generations in flight
+  constexpr int kEpiWarps = PAIR ? 4 : 8;
+
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int range = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, mgroup = blockIdx.y;
   const int t0 = (int)(((int64_t)p.tiles_total * range) / p.num_ranges);
   const int t1 = (int)(((int64_t)p.tiles_total * (range + 1)) / p.num_ranges);
   const int ntiles = t1 - t0;
-  const int q0 = mgroup * (kDtMT * 128);
-  const int n_act = min(kDtMT, (p.nq - q0 + 127) / 128);  // active 128-query tiles of this CTA
+  const int q0 = mgroup * (kDtMT * 128) + (PAIR ? (int)rank * 128 : 0);
+  // active 128-query tiles: a pair always runs its one M = 256 MMA (rows past nq are TMA zero fill)
+  const int n_act = PAIR ? 1 : min(kDtMT, (p.nq - q0 + 127) / 128);
   const int kblocks = p.d / kDtBK;
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-  uint8_t* stages = sm;  // kDtStages x [A0 | A1 | B]
-  uint64_t* sort_scratch = reinterpret_cast<uint64_t*>(stages + kDtStages * kDtStageBytes);  // [8 warps][256]
-  uint64_t* bars = sort_scratch + 8 * kDtCap;
-  uint64_t* full = bars;                  // kDtStages
-  uint64_t* empty = full + kDtStages;     // kDtStages
-  uint64_t* acc_full = empty + kDtStages;   // 1
-  uint64_t* acc_empty = acc_full + 1;       // 1
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  uint8_t* stages = sm;  // kStages x [A tiles | B]
+  uint64_t* sort_scratch = reinterpret_cast<uint64_t*>(stages + kStages * kStageBytes);  // [kEpiWarps][kDtCap]
+  uint64_t* bars = sort_scratch + kEpiWarps * kDtCap;
+  uint64_t* full = bars;                      // kStages (pair: the leader's count both CTAs' bytes)
+  uint64_t* empty = full + kStages;           // kStages
+  uint64_t* acc_full = empty + kStages;       // kAccBufs
+  uint64_t* acc_empty = acc_full + kAccBufs;  // kAccBufs (pair: the leader's collect both CTAs' epilogue warps)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + kAccBufs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < kDtStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 4 * n_act);  // the epilogue warps of the active sets
+    for (int b = 0; b < kAccBufs; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], PAIR ? 2 * 4 : 4 * n_act);  // the epilogue warps that drain one accumulator generation
+    }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr, 512);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_cta2(tmem_ptr, 512);
+      tmem_relinquish_cta2();
+    } else {
+      tmem_alloc(tmem_ptr, 512);
+      tmem_relinquish();
+    }
   }
   tc5_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc5_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0 && ntiles > 0) {
-      tma_prefetch_desc(&map_q);
-      tma_prefetch_desc(&map_c);
-      uint64_t pol_keep, pol_stream;
-      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-      asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_stream));
+    // One lane per box of a stage (A tile(s), B tile): a single issuing thread spends ~0.3-0.5 us per TMA
+    // instruction (barrier round trip + issue), which is more than a K block's worth of MMAs.
+    const int nbox = PAIR ? 2 : n_act + 1;
+    if (lane < nbox && ntiles > 0) {
+      tma_prefetch_desc(lane == nbox - 1 ? &map_c : &map_q);
+      uint64_t pol;
+      if (lane == nbox - 1)
+        asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));  // corpus: streamed
+      else
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));    // queries: re-read per tile
       int it = 0;
       for (int t = t0; t < t1; ++t) {
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const int s = it % kDtStages;
-          const uint32_t ph = (uint32_t)(it / kDtStages) & 1u;
+          const int s = it % kStages;
+          const uint32_t ph = (uint32_t)(it / kStages) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
-          uint8_t* st = stages + (size_t)s * kDtStageBytes;
-          mbar_arrive_expect_tx(&full[s], (uint32_t)n_act * kDtABytes + kDtBBytes);
-          for (int a = 0; a < n_act; ++a) tma_load_2d(st + a * kDtABytes, &map_q, kb * kDtBK, q0 + a * 128, &full[s], pol_keep);
-          tma_load_2d(st + kDtMT * kDtABytes, &map_c, kb * kDtBK, t * kDtBN, &full[s], pol_stream);
+          uint8_t* st = stages + (size_t)s * kStageBytes;
+          if (PAIR) {
+            // both CTAs' bytes land on the LEADER's barrier; only the leader posts the expectation
+            if (rank == 0 && lane == 0) mbar_arrive_expect_tx(&full[s], 2u * kStageBytes);
+            const uint32_t lead = mapa_u32(smem_u32(&full[s]), 0);
+            if (lane == 0)
+              tma_load_2d_cta2(st, &map_q, kb * kDtBK, q0, lead, pol);
+            else
+              tma_load_2d_cta2(st + kDtABytes, &map_c, kb * kDtBK, t * kDtBN + (int)rank * (int)kBRows, lead, pol);
+          } else {
+            if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)n_act * kDtABytes + kBBytes);
+            __syncwarp((1u << nbox) - 1u);
+            if (lane < nbox - 1)
+              tma_load_2d(st + lane * kDtABytes, &map_q, kb * kDtBK, q0 + lane * 128, &full[s], pol);
+            else
+              tma_load_2d(st + kMT * kDtABytes, &map_c, kb * kDtBK, t * kDtBN, &full[s], pol);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && ntiles > 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BF16, 128, kDtBN);
+    // ------------------------------------------------------------------ MMA issuer (pair: leader only)
+    if (lane == 0 && ntiles > 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BF16, PAIR ? 256 : 128, kDtBN);
       int it = 0;
       for (int t = 0; t < ntiles; ++t) {
-        mbar_wait(acc_empty, ((uint32_t)t & 1u) ^ 1u);  // epilogue has drained the previous tile
+        const int b = PAIR ? (t & 1) : 0;
+        const int use = PAIR ? (t >> 1) : t;  // uses of accumulator generation b so far
+        mbar_wait(&acc_empty[b], ((uint32_t)use & 1u) ^ 1u);  // the epilogue has drained it
         tc5_fence_after();
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const int s = it % kDtStages;
-          const uint32_t ph = (uint32_t)(it / kDtStages) & 1u;
+          const int s = it % kStages;
+          const uint32_t ph = (uint32_t)(it / kStages) & 1u;
           mbar_wait(&full[s], ph);
           tc5_fence_after();
-          uint8_t* st = stages + (size_t)s * kDtStageBytes;
-          const uint64_t db = umma_smem_desc_sw128(smem_u32(st + kDtMT * kDtABytes));
-          for (int a = 0; a < n_act; ++a) {
-            const uint64_t da = umma_smem_desc_sw128(smem_u32(st + a * kDtABytes));
+          uint8_t* st = stages + (size_t)s * kStageBytes;
+          const uint64_t db = umma_smem_desc_sw128(smem_u32(st + kMT * kDtABytes));
+          if (PAIR) {
+            const uint64_t da = umma_smem_desc_sw128(smem_u32(st));
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              umma_f16_ss(tmem_base + (uint32_t)a * kDtBN, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
-                          (kb | kk) != 0 ? 1u : 0u);
+              umma_f16_ss_cta2(tmem_base + (uint32_t)b * kDtBN, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
+                               (kb | kk) != 0 ? 1u : 0u);
+            umma_commit_cta2(&empty[s], 0b11);
+          } else {
+            for (int a = 0; a < n_act; ++a) {
+              const uint64_t da = umma_smem_desc_sw128(smem_u32(st + a * kDtABytes));
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_f16_ss(tmem_base + (uint32_t)a * kDtBN, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
+                            (kb | kk) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty[s]);
           }
-          umma_commit(&empty[s]);
         }
-        umma_commit(acc_full);
+        if (PAIR) umma_commit_cta2(&acc_full[b], 0b11); else umma_commit(&acc_full[b]);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + kEpiWarps) {
     // ------------------------------------------------------------------ epilogue: fused per-query top-k
     const int set = (warp - 4) >> 2, quarter = warp & 3;
     if (set < n_act && ntiles > 0) {
-      const int lq = set * 128 + quarter * 32 + lane;  // query within the CTA's group
+      const int lq = set * 128 + quarter * 32 + lane;  // query within this CTA's tiles
       const int query = q0 + lq;
       const bool valid = query < p.nq;
       uint64_t* my_sort = sort_scratch + (size_t)(warp - 4) * kDtCap;
-      uint64_t* my_cand =
-          p.cand + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * (kDtMT * 128) + lq) * kDtCap;
+      // candidate buffer of this (range, query): the CTA index is unique per (range, group, rank)
+      uint64_t* my_cand = p.cand + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * (kMT * 128) + lq) * kDtCap;
       // query scale for cosine (the corpus side is inv_norm[] or unit rows)
       float q_scale = 1.f;
       if (p.metric == 1 && valid) {
@@ -202,8 +259,16 @@ __global__ void __launch_bounds__(kDtThreads, 1)
       // A range sees only 1/ranges of the corpus, so thr_local alone lets ~k/rows_seen of the rows through;
       // T behaves like the k-th best of everything all ranges have seen and cuts that by an order of magnitude.
       float thr_local = -CUDART_INF_F, thr_cross = -CUDART_INF_F, thr = -CUDART_INF_F;
-      float tm0 = -CUDART_INF_F, tm1 = -CUDART_INF_F, tm2 = -CUDART_INF_F, tm3 = -CUDART_INF_F;  // best 4 scores seen
+      float tm[kDtMaxGm];  // best scores seen, descending (registers: every index below is static)
+#pragma unroll
+      for (int j = 0; j < kDtMaxGm; ++j) tm[j] = -CUDART_INF_F;
       const int gm = p.gm;
+      auto gm_th = [&]() {
+        float r = tm[0];
+#pragma unroll
+        for (int j = 1; j < kDtMaxGm; ++j) r = (gm == j + 1) ? tm[j] : r;
+        return r;
+      };
       uint32_t* my_gthr = p.gthr + (size_t)range * p.nq + (valid ? query : 0);
       const int cross_every = max(1, p.num_ranges / 32);  // tiles between refreshes of thr_cross
       int cnt = 0;
@@ -231,11 +296,15 @@ __global__ void __launch_bounds__(kDtThreads, 1)
         }
       };
 
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)set * kDtBN;
+      const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t lead_acc_empty = PAIR ? mapa_u32(smem_u32(acc_empty), 0) : 0u;
       uint32_t va[32], vb[32];
       for (int t = 0; t < ntiles; ++t) {
-        mbar_wait(acc_full, (uint32_t)t & 1u);
+        const int b = PAIR ? (t & 1) : 0;
+        const int use = PAIR ? (t >> 1) : t;
+        mbar_wait(&acc_full[b], (uint32_t)use & 1u);
         tc5_fence_after();
+        const uint32_t taddr = tlane + (uint32_t)(PAIR ? b : set) * kDtBN;
         const int64_t row_base = (int64_t)(t0 + t) * kDtBN;
         auto consume = [&](uint32_t (&v)[32], int ch) {
           const int64_t r0 = row_base + ch * 32;
@@ -270,17 +339,22 @@ __global__ void __launch_bounds__(kDtThreads, 1)
                   cbest = fmaxf(cbest, s);
                 }
               }
-              // Keep the best four scores sorted and publish the gm-th when it moves.  One insertion per chunk
-              // (its best appended row) keeps this out of the unrolled loop — 32 inlined copies pushed the kernel
-              // out of the instruction cache; a second top-gm row inside the same 32 rows only makes the bound
-              // looser, never wrong.
-              if (gm > 0 && cbest > tm3) {
-                const float before = gm == 1 ? tm0 : (gm == 2 ? tm1 : (gm == 3 ? tm2 : tm3));
-                tm3 = cbest;
-                if (tm3 > tm2) { const float x = tm2; tm2 = tm3; tm3 = x; }
-                if (tm2 > tm1) { const float x = tm1; tm1 = tm2; tm2 = x; }
-                if (tm1 > tm0) { const float x = tm0; tm0 = tm1; tm1 = x; }
-                const float after = gm == 1 ? tm0 : (gm == 2 ? tm1 : (gm == 3 ? tm2 : tm3));
+              // Keep the best scores sorted and publish the gm-th when it moves.  One insertion per chunk (its
+              // best appended row) keeps this out of the unrolled loop — 32 inlined copies pushed the kernel out of
+              // the instruction cache; a second top-gm row inside the same 32 rows only makes the bound looser,
+              // never wrong.
+              if (gm > 0 && cbest > tm[kDtMaxGm - 1]) {
+                const float before = gm_th();
+                tm[kDtMaxGm - 1] = cbest;
+#pragma unroll
+                for (int j = kDtMaxGm - 1; j > 0; --j) {
+                  if (tm[j] > tm[j - 1]) {
+                    const float x = tm[j - 1];
+                    tm[j - 1] = tm[j];
+                    tm[j] = x;
+                  }
+                }
+                const float after = gm_th();
                 if (after > before) __stcg(my_gthr, f32_orderable(after));
               }
             }
@@ -298,14 +372,16 @@ __global__ void __launch_bounds__(kDtThreads, 1)
           } else {
             tc5_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty);
+            if (lane == 0) {
+              if (PAIR) mbar_arrive_cluster(lead_acc_empty + (uint32_t)b * 8u); else mbar_arrive(&acc_empty[b]);
+            }
           }
           consume(vb, ch + 1);
           if (ch + 2 < kDtBN / 32) tmem_ld_wait(va);
         }
         // The accumulators went back to the MMA warp above, so compaction runs while the tensor core works on
         // the next tile.  Done inside the tile it sat on the critical path: the MMA restarts only when ALL
-        // eight warps have drained, and some warp compacts in almost every tile.
+        // the warps have drained, and some warp compacts in almost every tile.
         uint32_t need = __ballot_sync(0xFFFFFFFFu, cnt > kDtCompactAt);
         while (need) {
           const int L = __ffs(need) - 1;
@@ -349,10 +425,10 @@ __global__ void __launch_bounds__(kDtThreads, 1)
   }
 
   tc5_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();  // pair: the peer may still read this CTA's tiles / barriers
   if (warp == 2) {
     tc5_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_cta2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -378,9 +454,11 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
                    int64_t* out_ids, cudaStream_t stream, int* launched, std::string* err) {
   *launched = 0;
   const int num_sms = tc5_num_sms(s);
-  const int mgroups = (nq + kDtMT * 128 - 1) / (kDtMT * 128);
+  static const int no_pair = getenv("RS_DENSE_NO_PAIR") ? 1 : 0;  // A/B switch for scripts/batch_bench.py
+  const bool pair = !no_pair && num_sms >= 2;
+  const int mgroups = (nq + kDtMT * 128 - 1) / (kDtMT * 128);  // 256 queries per CTA / per CTA pair
   const int tiles_total = (int)((n + kDtBN - 1) / kDtBN);
-  int ranges = num_sms / mgroups;
+  int ranges = (pair ? num_sms / 2 : num_sms) / mgroups;
   if (ranges < 1) ranges = 1;
   if (ranges > tiles_total) ranges = tiles_total;
   while ((long long)ranges * k > 16384) --ranges;  // rs_topk_merge limit
@@ -395,7 +473,7 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
   {
     const uint64_t dims[2] = {(uint64_t)d, (uint64_t)n};
     const uint64_t strides[1] = {(uint64_t)d * 2};
-    const uint32_t box[2] = {kDtBK, (uint32_t)kDtBN};
+    const uint32_t box[2] = {kDtBK, (uint32_t)(pair ? kDtBN / 2 : kDtBN)};  // a pair's CTA stages half of the tile
     if (!tc5_encode(s, &map_c, dtype, 2, corpus, dims, strides, box, err)) return -2;
   }
   const size_t cand_bytes = (size_t)ranges * mgroups * (kDtMT * 128) * kDtCap * sizeof(uint64_t);
@@ -425,7 +503,7 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
   kp.gthr = reinterpret_cast<uint32_t*>(ws + cand_bytes + ls_bytes + li_bytes);
   static const int cross_off = getenv("RS_DENSE_NO_CROSS_THR") ? 1 : 0;  // A/B switch for scripts/batch_bench.py
   const int gm = (k + ranges - 1) / ranges;
-  kp.gm = (ranges > 1 && gm <= 4 && !cross_off) ? gm : 0;
+  kp.gm = (ranges > 1 && gm <= kDtMaxGm && !cross_off) ? gm : 0;
   if (kp.gm > 0) {
     cudaError_t me = cudaMemsetAsync(kp.gthr, 0, gt_bytes, stream);
     if (me != cudaSuccess) {
@@ -433,22 +511,33 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
       return -3;
     }
   }
-  const size_t smem = 1024 + (size_t)kDtStages * kDtStageBytes + 8 * kDtCap * sizeof(uint64_t) + 256;
-  dim3 grid(ranges, mgroups);
+  const size_t stage_bytes = pair ? (size_t)(kDtABytes + kDtBBytes / 2) : (size_t)kDtStageBytes;
+  const size_t smem = 1024 + (size_t)(pair ? kDtStagesPair : kDtStages) * stage_bytes +
+                      (size_t)(pair ? 4 : 8) * kDtCap * sizeof(uint64_t) + 256;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = pair ? dim3(2 * ranges, mgroups) : dim3(ranges, mgroups);
+  cfg.blockDim = dim3(pair ? kDtThreadsPair : kDtThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pair ? 1 : 0;
   cudaError_t e;
-  if (dtype == 1) {
-    e = cudaFuncSetAttribute(dense_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) {
-      dense_tc5_kernel<true><<<grid, kDtThreads, smem, stream>>>(map_q, map_c, kp);
-      e = cudaGetLastError();
-    }
-  } else {
-    e = cudaFuncSetAttribute(dense_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) {
-      dense_tc5_kernel<false><<<grid, kDtThreads, smem, stream>>>(map_q, map_c, kp);
-      e = cudaGetLastError();
-    }
+#define RS_DT_LAUNCH(BF, PR)                                                                                        \
+  {                                                                                                                 \
+    e = cudaFuncSetAttribute(dense_tc5_kernel<BF, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, dense_tc5_kernel<BF, PR>, map_q, map_c, kp);                 \
   }
+  if (dtype == 1) {
+    if (pair) RS_DT_LAUNCH(true, true) else RS_DT_LAUNCH(true, false)
+  } else {
+    if (pair) RS_DT_LAUNCH(false, true) else RS_DT_LAUNCH(false, false)
+  }
+#undef RS_DT_LAUNCH
   if (e != cudaSuccess) {
     *err = cudaGetErrorString(e);
     return -3;
