@@ -13,8 +13,10 @@ queries of the step, ONE NCCL all-gather moves the step's k (id, score) pairs an
 produces the global top-k on every rank.
 
   value     queries/s, inputs resident in HBM, CUDA events, max over ranks
-  e2e       the same metric through the per-request C-ABI call rs_dense_topk_host: host query in,
-            host (score, id) out, H2D + D2H + synchronise inside the timed region, once per query
+  e2e       the same metric through the public host entry point (rs_dense_topk_host at N = 1, the sharded index
+            at N > 1): the step's queries start in pinned host memory, its (score, id) pairs end in host memory,
+            H2D + D2H + synchronise inside the timed region once per step; e2e.per_request is the same with one
+            call, copy pair and synchronise per query (one request in flight)
   roofline  dense_scan_kernel: algorithmic bytes per launch / average launch duration (events over
             the timed region / launches) vs MEASURED_PEAKS.json hbm_gbs
   cpu_baseline / --impl reference
@@ -274,40 +276,62 @@ def run_b200(args):
     qps = nq * args.steps / (elapsed_ms * 1e-3)
     log(f"value {qps:.1f} q/s; end-to-end leg")
 
-    # ---- end to end: per-request host call, H2D + kernel + D2H + sync per query
-    out_s = torch.empty(1, k, dtype=torch.float32).pin_memory()
-    out_i = torch.empty(1, k, dtype=torch.int64).pin_memory()
-    q_dev = torch.empty(1, DIM, dtype=torch.float16, device=dev)
+    # ---- end to end: the step's queries start in pinned host memory and its results end in host memory, with
+    # the copies and the synchronise inside the timed region.
+    #   e2e.value        one public call per STEP: the 64 queries go up in one H2D copy, 64 single-query scans
+    #                    (N > 1: + all-gather + merge), the 64 x k pairs come back, one synchronise
+    #   e2e.per_request  one public call per QUERY, each with its own H2D, D2H and synchronise (a latency-bound
+    #                    serving loop with a single request in flight)
+    out_s = torch.empty(nq, k, dtype=torch.float32).pin_memory()
+    out_i = torch.empty(nq, k, dtype=torch.int64).pin_memory()
+    out_s1 = torch.empty(1, k, dtype=torch.float32).pin_memory()
+    out_i1 = torch.empty(1, k, dtype=torch.int64).pin_memory()
+    q_dev = torch.empty(nq, DIM, dtype=torch.float16, device=dev)
 
     def step_e2e():
+        if world == 1:
+            # the C-ABI host entry point: H2D(queries) -> scans -> (score, id) pairs in host memory -> synchronise
+            eng.dense_topk_host(corpus, queries_host, k, mask_dev=mask, metric=_ffi.RS_METRIC_COSINE,
+                                id_base=lo, out_scores=out_s, out_ids=out_i)
+        else:
+            q_dev.copy_(queries_host, non_blocking=True)
+            s, i = index.search(q_dev, k, mask)
+            out_s.copy_(s, non_blocking=True)
+            out_i.copy_(i, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    def step_per_request():
         for j in range(nq):
             if world == 1:
-                # the C-ABI host entry point: H2D(query) -> scan -> D2H(k pairs) -> synchronise
                 eng.dense_topk_host(corpus, queries_host[j], k, mask_dev=mask, metric=_ffi.RS_METRIC_COSINE,
-                                    id_base=lo, out_scores=out_s, out_ids=out_i)
+                                    id_base=lo, out_scores=out_s1, out_ids=out_i1)
             else:
-                # sharded request: H2D(query) -> local scan -> all-gather -> merge -> D2H -> synchronise
-                q_dev.copy_(queries_host[j: j + 1], non_blocking=True)
-                s, i = index.search(q_dev, k, mask)
-                out_s.copy_(s, non_blocking=True)
-                out_i.copy_(i, non_blocking=True)
+                q_dev[:1].copy_(queries_host[j: j + 1], non_blocking=True)
+                s, i = index.search(q_dev[:1], k, mask)
+                out_s1.copy_(s, non_blocking=True)
+                out_i1.copy_(i, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
 
-    for _ in range(max(1, min(args.warmup, 2))):
-        step_e2e()
-    barrier()
-    e2e_steps = max(2, args.steps // 4)
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    barrier()
-    e2e_dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_dt = float(t.item())
-    e2e_qps = nq * e2e_steps / e2e_dt
-    log(f"e2e {e2e_qps:.1f} q/s; sanity check, extras, cpu baseline")
+    def timed_host_loop(fn, steps):
+        for _ in range(max(1, min(args.warmup, 2))):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return nq * steps / dt
+
+    e2e_steps = args.steps
+    e2e_qps = timed_host_loop(step_e2e, e2e_steps)
+    per_request_steps = max(2, args.steps // 4)
+    per_request_qps = timed_host_loop(step_per_request, per_request_steps)
+    log(f"e2e {e2e_qps:.1f} q/s per step call, {per_request_qps:.1f} q/s per request; sanity check, extras, cpu baseline")
 
     # ---- sanity check of the timed configuration against an independent torch computation on the
     # GPU (not the oracle, not our kernel): fp32 matmul + mask + torch.topk over this rank's shard
@@ -318,6 +342,13 @@ def run_b200(args):
         ref = torch.where(torch.from_numpy(bits).to(dev), ref, torch.full_like(ref, float("-inf")))
         rs, ri = torch.topk(ref, k)
         check = bool(torch.equal(ri + lo, i[0]) and torch.allclose(rs, s[0], rtol=1e-3, atol=1e-6))
+    # ... and the end-to-end leg returned, in host memory, what the device-resident leg computes (every rank takes
+    # part: with N > 1 both legs contain the all-gather)
+    step_e2e()
+    s_all, i_all = step_device()
+    same = bool(torch.equal(i_all.cpu(), out_i) and torch.allclose(s_all.cpu(), out_s, rtol=1e-6, atol=0))
+    if rank == 0:
+        check = check and same
 
     # ---- roofline of the scan kernel
     peaks = {}
@@ -368,7 +399,9 @@ def run_b200(args):
                        "l2": (f"inputs larger than L2: every query re-reads its {rows_local * DIM * 2 / 1e6:.0f} MB shard "
                               "(126 MB L2, loads carry an evict_first hint)")},
             "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": nq * DIM * 2, "d2h_bytes_per_step": nq * k * 12,
-                    "steps": e2e_steps},
+                    "steps": e2e_steps, "calls_per_step": 1,
+                    "per_request": {"value": per_request_qps, "unit": UNIT, "calls_per_step": nq,
+                                    "steps": per_request_steps}},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
             "parity_spot_check": check, "extra": extra,
         }

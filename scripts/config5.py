@@ -30,6 +30,10 @@ ap.add_argument("--k1", type=int, default=1000)
 ap.add_argument("--k2", type=int, default=10)
 ap.add_argument("--check", action="store_true")
 args = ap.parse_args()
+if args.check:  # the oracle gathers corpus and pool on every rank: keep --check small whatever else was passed
+    args.rows_per_gpu = min(args.rows_per_gpu, 200_000)
+    args.pool_docs = min(args.pool_docs, 20_000)
+    args.queries = min(args.queries, 6)
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
