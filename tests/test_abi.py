@@ -28,6 +28,20 @@ def test_header_symbols_are_exported_and_bound():
     assert sorted(_ffi.SIGNATURES) == syms
 
 
+def test_header_enums_match_the_python_constants():
+    """Every enumerator of rag_b200.h (status codes, dtypes, metrics, kernel families) has the same value in _ffi.py."""
+    text = open(os.path.join(ROOT, "include", "rag_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    found = {}
+    for body in re.findall(r"enum\s*\w*\s*\{(.*?)\}", text, flags=re.S):
+        for name, value in re.findall(r"(RS_[A-Z0-9_]+)\s*=\s*(-?\d+)", body):
+            found[name] = int(value)
+    assert {"RS_OK", "RS_F16", "RS_METRIC_COSINE", "RS_MAXSIM_TCGEN05_CAND", "RS_DENSE_TCGEN05"} <= set(found)
+    for name, value in found.items():
+        assert hasattr(_ffi, name), f"{name} of rag_b200.h is missing in _ffi.py"
+        assert getattr(_ffi, name) == value, f"{name}: header {value}, _ffi.py {getattr(_ffi, name)}"
+
+
 def test_library_loads_and_reports_abi_version():
     lib = rag.load_library()
     assert lib.rs_abi_version() == 1

@@ -60,6 +60,64 @@ def test_mask_edge_patterns(engine):
     _check(engine, corpus, query, 10, one)  # fewer passing rows than k -> (-inf, -1) padding
 
 
+@pytest.mark.parametrize("n,d,k", [(200_003, 64, 10), (150_000, 128, 33), (400_001, 256, 32), (90_000, 1024, 32),
+                                   (90_000, 1024, 33), (33, 1024, 10), (4737, 1024, 10)])
+def test_guided_work_distribution_shapes(engine, n, d, k):
+    """Shapes that exercise the scan's work counter and both cross-CTA merges: small d (a grab is several mask words,
+    32-row tiles), many grabs per CTA, k on both sides of the tournament limit (32), fewer words than SMs."""
+    corpus, query = make_dense_case(77 + n, n, d)
+    bits = bernoulli_mask(n, n, 0.6)
+    _check(engine, corpus, query, k, bits)
+    _check(engine, corpus, query, k)
+
+
+def test_back_to_back_launches_share_nothing(engine):
+    """40 queries in one call (chained launches under programmatic dependent launch, rotating work counters and
+    alternating workspaces), three times over: every query's result equals its own single-launch result."""
+    n, d, k, nq = 60_000, 256, 10, 40
+    corpus, _ = make_dense_case(5, n, d)
+    g = torch.Generator().manual_seed(6)
+    queries = torch.randn(nq, d, generator=g).half()
+    dev = engine.device
+    c, q = corpus.to(dev), queries.to(dev)
+    engine.set_dense_impl(_ffi.RS_DENSE_SCAN)
+    try:
+        single = [engine.dense_topk(c, q[j], k) for j in range(nq)]
+        for _ in range(3):
+            s, i = engine.dense_topk(c, q, k)
+            for j in range(nq):
+                assert torch.equal(i[j], single[j][1][0]) and torch.equal(s[j], single[j][0][0])
+    finally:
+        engine.set_dense_impl(_ffi.RS_DENSE_AUTO)
+
+
+def test_scan_trace_records_every_phase(engine):
+    """rs_set_scan_trace: every CTA stamps its phases in order; exactly one CTA (the last to publish) runs the merge."""
+    n, d, k = 300_000, 1024, 10
+    corpus, query = make_dense_case(8, n, d)
+    dev = engine.device
+    c, q = corpus.to(dev), query.to(dev)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    trace = torch.zeros(8, sms, 8, dtype=torch.int64, device=dev)
+    engine.set_dense_impl(_ffi.RS_DENSE_SCAN)
+    engine.set_scan_trace(trace)
+    try:
+        s, i = engine.dense_topk(c, q, k)
+        torch.cuda.synchronize()
+    finally:
+        engine.set_scan_trace(None)
+        engine.set_dense_impl(_ffi.RS_DENSE_AUTO)
+    t = trace.cpu()
+    used = [b for b in range(8) if int(t[b, :, 0].max()) > 0]
+    assert len(used) == 1
+    tt = t[used[0]]
+    assert (tt[:, 0] > 0).all()                       # one CTA per SM
+    assert (tt[:, 1:7] >= tt[:, 0:6]).all()           # phases in order
+    assert int((tt[:, 7] > 0).sum()) == 1             # a single merging CTA
+    s2, i2 = engine.dense_topk(c, q, k)               # tracing does not change the result
+    assert torch.equal(i, i2) and torch.equal(s, s2)
+
+
 def test_inner_product_and_inv_norm(engine):
     n, d = 9000, 1024
     corpus, query = make_dense_case(5, n, d, normalise=False)
