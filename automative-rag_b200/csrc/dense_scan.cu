@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
     for (int left = NW; left > 0; left -= batch_max) issue_marker(min(left, batch_max), kSlotEnd);  // END for all
   } else if (warp < NW) {
     // ------------------------------------------------------------------ consumer warps
-    TopKBuffer buf{keys, thr, cnt, p.buf_cap, p.k, (int)threadIdx.x, consumer_threads, kConsumerBar};
+    TopKBuffer buf{keys, thr, cnt, p.buf_cap, p.buf_hw, p.k, (int)threadIdx.x, consumer_threads, kConsumerBar};
     buf.init();
 
     // query stays packed 16-bit in registers; lane owns elements c*256 + lane*8 .. +7
@@ -336,8 +336,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
     }
     const float* inv_norm = p.inv_norm;
     const int nvec = p.d >> 3;  // 16-byte vectors per row
-    // appends per round <= warps * tile_rows; the buffer tolerates C/2 between checks
-    const int rounds_per_check = max(1, (p.buf_cap >> 1) / (NW * tile_rows));
+    // appends per round <= warps * tile_rows; the buffer tolerates C - hw between checks
+    const int rounds_per_check = p.rounds_per_check;
 
     const bool two_slots = S == 2 * NW;  // this warp alternates between slots warp and warp + NW
     scan_trace(p, 2);
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
       // The buffer already holds this CTA's own top-k with the matching threshold; stream the
       // other CTAs' sorted lists through it.  Thread t walks list t (+lists_per_pass, ...); a list is
       // abandoned at its first key <= threshold (lists are sorted).
-      const int lists_per_pass = min(consumer_threads, buf.C >> 1);  // <= C/2 appends between checks
+      const int lists_per_pass = min(consumer_threads, buf.slack());  // appends between two checks
       constexpr int KB = 8;  // keys fetched per thread per batch: KB independent L2 loads, one latency
       for (int base = 0; base < (int)gridDim.x; base += lists_per_pass) {
         const int list = base + threadIdx.x;
@@ -567,34 +567,47 @@ int scan_tile_rows(int d) {
   return tr;
 }
 
-static size_t scan_fixed_smem(int k) {
-  return (size_t)TopKBuffer::capacity_for(k) * 8 + 2 * kScanMaxStages * 8 + 8 + 16 + kScanMaxStages * 4 +
-         kScanMaxStages * 32 * 4 + kRowQueue * 4;
-}
+// Shared-memory plan of a launch: the top-k buffer first, the tile ring in what is left.
+struct ScanPlan {
+  int tile_rows, consumers, stages, buf_cap, buf_hw, rounds_per_check;
+  size_t smem;
+};
 
-// consumers (<= 13) and ring slots (consumers x 1 or x 2) that fit beside the top-k buffer
-static void scan_ring(int d, int k, int& consumers, int& stages) {
+static ScanPlan scan_plan(int d, int k) {
   static const int max_slots = env_int("RS_SCAN_STAGES", kScanMaxStages);
-  const size_t tile_bytes = (size_t)scan_tile_rows(d) * d * 2;
+  ScanPlan pl{};
+  pl.tile_rows = scan_tile_rows(d);
+  // the buffer is checked every `rounds_per_check` consumer rounds; a round appends at most one key per staged
+  // row (<= 13 warps x tile_rows): about 256 appends between checks
+  const int per_round = kScanMaxWarps * pl.tile_rows;
+  pl.rounds_per_check = 256 / per_round > 1 ? 256 / per_round : 1;
+  const int slack = per_round * pl.rounds_per_check;
+  pl.buf_cap = TopKBuffer::capacity_for(k, slack);
+  pl.buf_hw = pl.buf_cap - slack;
+  const size_t fixed = (size_t)pl.buf_cap * 8 + 2 * kScanMaxStages * 8 + 8 + 16 + kScanMaxStages * 4 +
+                       kScanMaxStages * 32 * 4 + kRowQueue * 4;
+  const size_t tile_bytes = (size_t)pl.tile_rows * d * 2;
   const size_t budget = 227 * 1024 - 1024;  // leave 1 KB for the runtime's reserved shared memory
-  int s = (int)((budget - scan_fixed_smem(k)) / tile_bytes);
+  int s = (int)((budget - fixed) / tile_bytes);
   s = s > kScanMaxStages ? kScanMaxStages : s;
   s = s > max_slots ? max_slots : s;
   if (s < 2) s = 2;
-  consumers = s < kScanMaxWarps ? s : kScanMaxWarps;
-  stages = consumers * (s / consumers);
+  // Two slots per consumer (one tile in flight while the other is reduced) as soon as 8 consumers can have
+  // them: 11 consumers x 2 slots beat 13 x 1 — bytes in flight matter more than the two extra warps.
+  if (s >= 16) {
+    pl.consumers = s / 2 < kScanMaxWarps ? s / 2 : kScanMaxWarps;
+    pl.stages = 2 * pl.consumers;
+  } else {
+    pl.consumers = s < kScanMaxWarps ? s : kScanMaxWarps;
+    pl.stages = pl.consumers;
+  }
+  pl.smem = (size_t)pl.stages * tile_bytes + fixed;
+  return pl;
 }
 
-int scan_stages(int d, int k) {
-  int c, s;
-  scan_ring(d, k, c, s);
-  return s;
-}
+int scan_stages(int d, int k) { return scan_plan(d, k).stages; }
 
-size_t scan_smem_bytes(int d, int k) {
-  const size_t tile_bytes = (size_t)scan_tile_rows(d) * d * 2;
-  return (size_t)scan_stages(d, k) * tile_bytes + scan_fixed_smem(k);
-}
+size_t scan_smem_bytes(int d, int k) { return scan_plan(d, k).smem; }
 
 // Smallest grab, in mask words: at least 64 KB of rows, so that the counter's round trip (~1 us)
 // stays hidden behind the ring (26 x 8 KB already issued ahead) also at the very end.
@@ -607,9 +620,13 @@ static int scan_unit_words(int d) {
 }
 
 cudaError_t launch_dense_scan(ScanParams p, int dtype, int num_sms, bool pdl, cudaStream_t stream) {
-  p.tile_rows = scan_tile_rows(p.d);
-  scan_ring(p.d, p.k, p.consumers, p.stages);
-  p.buf_cap = TopKBuffer::capacity_for(p.k);
+  const ScanPlan pl = scan_plan(p.d, p.k);
+  p.tile_rows = pl.tile_rows;
+  p.consumers = pl.consumers;
+  p.stages = pl.stages;
+  p.buf_cap = pl.buf_cap;
+  p.buf_hw = pl.buf_hw;
+  p.rounds_per_check = pl.rounds_per_check;
   static const int l2_policy = env_int("RS_SCAN_L2_POLICY", 0);
   p.l2_policy = l2_policy;
   const int64_t num_words = (p.n + 31) / 32;  // a mask word covers 32 rows
@@ -622,7 +639,7 @@ cudaError_t launch_dense_scan(ScanParams p, int dtype, int num_sms, bool pdl, cu
   int64_t first = num_words / ((int64_t)grid * 4);
   first = first > p.grab_max ? p.grab_max : first;
   p.first_words = first < p.unit_words ? 0 : (int32_t)first;
-  const size_t smem = scan_smem_bytes(p.d, p.k);
+  const size_t smem = pl.smem;
   if (dtype == 0) return launch_scan_t<__half>(p, grid, smem, pdl, stream);
   return launch_scan_t<__nv_bfloat16>(p, grid, smem, pdl, stream);
 }

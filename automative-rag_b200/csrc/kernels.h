@@ -23,7 +23,9 @@ struct ScanParams {
   int32_t tile_rows;       // filled by the launcher
   int32_t stages;          // ring slots, filled by the launcher
   int32_t consumers;       // consumer warps, filled by the launcher (stages is a multiple of it)
-  int32_t buf_cap;         // filled by the launcher
+  int32_t buf_cap;         // top-k buffer capacity, filled by the launcher
+  int32_t buf_hw;          // its high-water mark (capacity - appends possible between two checks)
+  int32_t rounds_per_check;  // consumer rounds between two buffer checks
   int32_t l2_policy;       // 0 evict_first (default), 1 normal, 2 evict_last
   unsigned long long* unit_counter;  // next unclaimed mask word of this launch; 0 on entry, reset by the merging CTA
   int32_t unit_words;      // smallest grab in mask words (32 rows each), filled by the launcher

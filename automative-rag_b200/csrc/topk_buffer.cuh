@@ -1,10 +1,12 @@
 // topk_buffer.cuh — CTA-level running top-k over a stream of u64 result keys.
 //
-// A shared-memory buffer of C = pow2 >= max(4k, 512) keys plus a threshold (the current
-// k-th best key).  Producers append only keys above the threshold; when the buffer passes its
-// high-water mark H = C/2 the CTA sorts it (bitonic, descending), keeps the best k and raises
-// the threshold.  The caller guarantees that no more than C - H keys are appended between two
-// `maybe_compact` calls (H >= k always holds), so appends never overflow.
+// A shared-memory buffer of C (a power of two) keys plus a threshold (the current k-th best key).
+// Producers append only keys above the threshold; when the buffer passes its high-water mark
+// H = C - slack the CTA sorts it (bitonic, descending), keeps the best k and raises the threshold.
+// The caller guarantees that no more than `slack` keys are appended between two `maybe_compact`
+// calls, so appends never overflow; C >= 1.5 k + slack leaves at least k/2 appends between two
+// compactions.  (The buffer shares the CTA's shared memory with the scan's tile ring: a first
+// version with C >= 4k cost k = 1000 half of the ring and 40 % of the scan's bandwidth.)
 //
 // This replaces a per-thread heap: after the first few hundred rows almost nothing beats the
 // threshold (expected appends ~ k * ln(rows / k)), so the common path is one compare per row.
@@ -17,18 +19,16 @@ struct TopKBuffer {
   uint64_t* keys;     // [C] shared
   uint64_t* thr;      // shared: current threshold key (0 = none yet)
   int* cnt;           // shared: number of valid keys
-  int C, k;
+  int C, hw, k;       // capacity, high-water mark (C - slack), list length
   int tid, nthreads;  // participating threads (named barrier `bar_id`)
   int bar_id;
 
-  __device__ __forceinline__ int high_water() const { return C >> 1; }
+  __device__ __forceinline__ int high_water() const { return hw; }
+  __device__ __forceinline__ int slack() const { return C - hw; }
 
-  static __host__ __device__ __forceinline__ int capacity_for(int k) {
-    // 4k: after a compaction (k survivors) there is room for >= k more appends before the next
-    // one, so a scan needs O(log(rows / k)) compactions; 2k would compact every few rows when k is
-    // just under a power of two.
+  static __host__ __device__ __forceinline__ int capacity_for(int k, int slack) {
     int c = 512;
-    while (c < 4 * k) c <<= 1;
+    while (c < k + k / 2 + slack) c <<= 1;
     return c;
   }
 
