@@ -437,7 +437,10 @@ bool tc5_dense_supported(const Tc5State* s, int64_t n, int d, int nq, int k, con
                          int64_t mask_stride_words) {
   (void)mask;
   if (!s) return false;
-  if (nq < 32 || n < kDtBN) return false;        // below that the scan loop is the better tool
+  // One batched pass over the corpus beats a loop of single-query scans from 4 queries on (1M x 1024 rows, k = 10:
+  // 0.60 vs 1.15 ms at 4 queries, 1.1 vs 9.2 ms at 32; profiles/r01_batch_crossover.txt).
+  static const int min_nq = getenv("RS_DENSE_TC_MIN_NQ") ? atoi(getenv("RS_DENSE_TC_MIN_NQ")) : 4;
+  if (nq < min_nq || n < kDtBN) return false;
   if (d % kDtBK != 0 || d < kDtBK) return false;
   if (k > 128) return false;
   if (mask_stride_words != 0) return false;      // one shared filter for the batch
@@ -455,7 +458,8 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
   *launched = 0;
   const int num_sms = tc5_num_sms(s);
   static const int no_pair = getenv("RS_DENSE_NO_PAIR") ? 1 : 0;  // A/B switch for scripts/batch_bench.py
-  const bool pair = !no_pair && num_sms >= 2;
+  // pairs cover 256 queries; up to 128 queries fit one CTA's single M tile, where a pair's second CTA would idle
+  const bool pair = !no_pair && num_sms >= 2 && nq > 128;
   const int mgroups = (nq + kDtMT * 128 - 1) / (kDtMT * 128);  // 256 queries per CTA / per CTA pair
   const int tiles_total = (int)((n + kDtBN - 1) / kDtBN);
   int ranges = (pair ? num_sms / 2 : num_sms) / mgroups;

@@ -217,7 +217,7 @@ int rs_dense_topk(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_
   if (impl == RS_DENSE_AUTO) impl = rs::tc5_dense_supported(h->tc5, n, d, nq, k, mask, mask_stride_words) ? RS_DENSE_TCGEN05 : RS_DENSE_SCAN;
   if (impl == RS_DENSE_TCGEN05) {
     if (!rs::tc5_dense_supported(h->tc5, n, d, nq, k, mask, mask_stride_words))
-      return fail(h, RS_ERR_UNSUPPORTED, "rs_dense_topk: tcgen05 batched path needs nq >= 32, n >= 256, d %% 64 == 0, k <= 128, one shared mask");
+      return fail(h, RS_ERR_UNSUPPORTED, "rs_dense_topk: tcgen05 batched path needs nq >= 4, n >= 256, d %% 64 == 0, k <= 128, one shared mask");
     int launched = 0;
     std::string err;
     int rc = rs::tc5_dense_topk(h->tc5, corpus, n, d, dtype, inv_norm, metric, queries, nq, mask, k, id_base, out_scores,

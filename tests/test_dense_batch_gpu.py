@@ -42,7 +42,9 @@ def _check_all(got_s, got_i, c, q, k, bits=None, metric=_ffi.RS_METRIC_COSINE, i
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("n,d,nq,k", [(256, 64, 32, 1), (1000, 128, 100, 10), (5000, 1024, 256, 100),
-                                      (70001, 1024, 300, 100), (20000, 512, 1024, 128), (300, 64, 33, 128)])
+                                      (70001, 1024, 300, 100), (20000, 512, 1024, 128), (300, 64, 33, 128),
+                                      (3000, 1024, 4, 10), (40_000, 512, 7, 100), (9000, 256, 31, 128),
+                                      (6000, 128, 129, 10)])
 def test_batched_matches_oracle(engine, dtype, n, d, nq, k):
     c, q = _case(n + nq, n, d, nq, dtype)
     s, i = _run(engine, c, q, k, _ffi.RS_DENSE_TCGEN05)
@@ -140,6 +142,10 @@ def test_batched_agrees_with_scan_and_auto_dispatch(engine):
     engine.set_dense_impl(_ffi.RS_DENSE_AUTO)
     engine.dense_topk(c.to(engine.device), q.to(engine.device), k)
     assert engine.last_dense_impl == _ffi.RS_DENSE_TCGEN05    # a batch goes to the tensor cores
+    engine.dense_topk(c.to(engine.device), q[:4].to(engine.device), k)
+    assert engine.last_dense_impl == _ffi.RS_DENSE_TCGEN05    # ... from four queries on (one pass over the corpus)
+    engine.dense_topk(c.to(engine.device), q[:3].to(engine.device), k)
+    assert engine.last_dense_impl == _ffi.RS_DENSE_SCAN       # fewer: a loop of HBM-bound scans
     engine.dense_topk(c.to(engine.device), q[:1].to(engine.device), k)
     assert engine.last_dense_impl == _ffi.RS_DENSE_SCAN       # a single query to the HBM-bound scan
 
