@@ -83,8 +83,9 @@ __device__ __forceinline__ void warp_sort_desc(uint64_t* keys, int n, int lane) 
   __syncwarp();
 }
 
-// PAIR = false: one CTA per (range, 256-query group), two 128-query UMMA tiles, both accumulators fill TMEM, so the
-//   epilogue and the MMAs of consecutive tiles alternate.
+// PAIR = false: one CTA per (range, 256-query group) with up to two 128-query UMMA tiles.  Two active tiles fill
+//   TMEM with their accumulators, so the epilogue and the MMAs of consecutive corpus tiles alternate; a single
+//   active tile (batches of <= 128 queries) leaves room for two accumulator generations and overlaps them.
 // PAIR = true: a CTA PAIR (2-wide cluster = the two SMs of a TPC) per (range, 256-query group) runs ONE
 //   tcgen05.mma.cta_group::2 of M = 256: each CTA stages its 128 queries and HALF of the 256 corpus rows (the tensor
 //   cores read the other half from the peer's shared memory), and holds its 128 x 256 accumulator in its own TMEM —
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(kDtThreads, 1)
   constexpr uint32_t kBRows = PAIR ? kDtBN / 2 : kDtBN;       // corpus rows staged by this CTA
   constexpr uint32_t kBBytes = kBRows * 128;
   constexpr uint32_t kStageBytes = kMT * kDtABytes + kBBytes;
-  constexpr int kAccBufs = PAIR ? 2 : 1;                      // accumulator generations in flight
+  constexpr int kAccBufs = 2;                                 // accumulator generations in flight (see dbuf)
   constexpr int kEpiWarps = PAIR ? 4 : 8;
 
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
@@ -114,6 +115,9 @@ __global__ void __launch_bounds__(kDtThreads, 1)
   // active 128-query tiles: a pair always runs its one M = 256 MMA (rows past nq are TMA zero fill)
   const int n_act = PAIR ? 1 : min(kDtMT, (p.nq - q0 + 127) / 128);
   const int kblocks = p.d / kDtBK;
+  // Two accumulator generations (the epilogue of tile t overlaps the MMAs of tile t+1) whenever a generation needs
+  // only 256 TMEM columns: always for pairs, and for single-CTA tiles when just one 128-query tile is active.
+  const bool dbuf = PAIR || n_act == 1;
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -196,8 +200,8 @@ __global__ void __launch_bounds__(kDtThreads, 1)
       constexpr uint32_t idesc = umma_idesc_f16(BF16, PAIR ? 256 : 128, kDtBN);
       int it = 0;
       for (int t = 0; t < ntiles; ++t) {
-        const int b = PAIR ? (t & 1) : 0;
-        const int use = PAIR ? (t >> 1) : t;  // uses of accumulator generation b so far
+        const int b = dbuf ? (t & 1) : 0;
+        const int use = dbuf ? (t >> 1) : t;  // uses of accumulator generation b so far
         mbar_wait(&acc_empty[b], ((uint32_t)use & 1u) ^ 1u);  // the epilogue has drained it
         tc5_fence_after();
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
@@ -219,8 +223,8 @@ __global__ void __launch_bounds__(kDtThreads, 1)
               const uint64_t da = umma_smem_desc_sw128(smem_u32(st + a * kDtABytes));
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
-                umma_f16_ss(tmem_base + (uint32_t)a * kDtBN, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
-                            (kb | kk) != 0 ? 1u : 0u);
+                umma_f16_ss(tmem_base + (uint32_t)(dbuf ? b : a) * kDtBN, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2),
+                            idesc, (kb | kk) != 0 ? 1u : 0u);
             }
             umma_commit(&empty[s]);
           }
@@ -300,11 +304,11 @@ __global__ void __launch_bounds__(kDtThreads, 1)
       const uint32_t lead_acc_empty = PAIR ? mapa_u32(smem_u32(acc_empty), 0) : 0u;
       uint32_t va[32], vb[32];
       for (int t = 0; t < ntiles; ++t) {
-        const int b = PAIR ? (t & 1) : 0;
-        const int use = PAIR ? (t >> 1) : t;
+        const int b = dbuf ? (t & 1) : 0;
+        const int use = dbuf ? (t >> 1) : t;
         mbar_wait(&acc_full[b], (uint32_t)use & 1u);
         tc5_fence_after();
-        const uint32_t taddr = tlane + (uint32_t)(PAIR ? b : set) * kDtBN;
+        const uint32_t taddr = tlane + (uint32_t)(dbuf ? b : set) * kDtBN;
         const int64_t row_base = (int64_t)(t0 + t) * kDtBN;
         auto consume = [&](uint32_t (&v)[32], int ch) {
           const int64_t r0 = row_base + ch * 32;

@@ -143,6 +143,8 @@ int rs_dense_topk_host(rs_handle* h, const void* corpus, int64_t n, int32_t d, i
  * leaves them: scores/ids [nlists, nq, k_in], list l starting at scores + l * score_list_stride
  * and ids + l * id_list_stride (strides in ELEMENTS; 0 = dense, i.e. nq * k_in), so the views
  * into the gathered wire buffer are consumed without a copy.  Entries with id < 0 are padding.
+ * Lists are expected in descending score order (what rs_dense_topk writes); other orders give the
+ * same result, only slower.
  * Output [nq, k_out] in (score desc, id asc) order, padded with (-inf, -1).
  * nlists * k_in <= 16384.
  */

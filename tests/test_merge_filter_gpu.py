@@ -36,6 +36,37 @@ def test_topk_merge_matches_oracle(engine, nl, nq, k_in, k_out):
     np.testing.assert_array_equal(s.cpu().numpy(), ws)
 
 
+@pytest.mark.parametrize("nl,nq,k_in,k_out,mode", [
+    (148, 3, 100, 100, "sorted"),      # the batched dense search: 148 ranges x top-100 (pruned: ~300 of 14800 keys sorted)
+    (37, 4, 100, 100, "sorted"),
+    (148, 2, 16, 10, "sorted"),        # k_out < k_in
+    (64, 2, 100, 10, "sorted"),
+    (100, 2, 100, 100, "unsorted"),    # the bound holds for any order: same result, less pruning
+    (120, 2, 100, 100, "sparse"),      # most lists empty or nearly empty -> the bound switches off
+    (16, 3, 1000, 1000, "ties"),       # heavy exact ties at the bound
+])
+def test_topk_merge_pruned_paths(engine, nl, nq, k_in, k_out, mode):
+    rng = np.random.default_rng(nl + k_in)
+    scores = rng.standard_normal((nl, nq, k_in)).astype(np.float32)
+    if mode == "ties":
+        scores = np.round(scores, 1)
+    if mode != "unsorted":
+        scores = np.sort(scores, axis=2)[:, :, ::-1].copy()
+    ids = rng.permutation(nl * nq * k_in).astype(np.int64).reshape(nl, nq, k_in) * 3
+    if mode == "sparse":
+        keep = rng.integers(0, 4, size=(nl, nq))            # 0..3 valid entries per list
+        for l in range(nl):
+            for q in range(nq):
+                scores[l, q, keep[l, q]:] = -np.inf
+                ids[l, q, keep[l, q]:] = -1
+        scores[0, :, :] = np.sort(rng.standard_normal((nq, k_in)).astype(np.float32), axis=1)[:, ::-1]
+        ids[0, :, :] = np.arange(10**6, 10**6 + nq * k_in).reshape(nq, k_in)
+    ws, wi = odense.merge_topk(scores, ids, k_out)
+    s, i = engine.topk_merge(torch.from_numpy(scores).to(engine.device), torch.from_numpy(ids).to(engine.device), k_out)
+    np.testing.assert_array_equal(i.cpu().numpy(), wi)
+    np.testing.assert_array_equal(s.cpu().numpy(), ws)
+
+
 def test_topk_merge_consumes_the_gathered_wire_buffer_in_place(engine):
     nq, k, world = 3, 10, 4
     rng = np.random.default_rng(0)
