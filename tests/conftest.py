@@ -18,3 +18,23 @@ def engine():
     import automative_rag_b200 as rag
 
     return rag.get_engine(0)
+
+
+@pytest.fixture(autouse=True)
+def _kernel_choice_back_to_auto(request):
+    """GPU tests force kernel families through the shared engine; every test starts and ends on AUTO so the files
+    behave the same in one pytest process (how the driver runs them) as one process per file."""
+    yield
+    if request.node.get_closest_marker("gpu") is None:
+        return
+    import torch
+
+    if not torch.cuda.is_available():
+        return
+    import automative_rag_b200 as rag
+    from automative_rag_b200 import _ffi
+
+    eng = rag.get_engine(0)
+    eng.set_dense_impl(_ffi.RS_DENSE_AUTO)
+    eng.set_maxsim_impl(_ffi.RS_MAXSIM_AUTO)
+    eng.set_scan_trace(None)
