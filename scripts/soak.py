@@ -19,7 +19,7 @@ while time.time() - t0 < budget:
     d = int(rng.choice([64, 128, 256, 1024]))
     n = int(rng.choice([1, 7, 33, 1000, 4097, 65_537, 150_000, 390_000]))
     k = int(rng.choice([1, 10, 37, 100, 1000]))
-    nq = int(rng.choice([1, 1, 3, 64]))
+    nq = int(rng.choice([1, 1, 3, 5, 40, 64, 200]))
     c = big[dt][:n, :d].contiguous()
     q = torch.randn(nq, d, generator=g, device=dev).to(dt)
     p = float(rng.choice([1.0, 1.0, 0.9, 0.5, 0.05, 0.0]))
@@ -42,8 +42,8 @@ while time.time() - t0 < budget:
         got = torch.gather(ref, 1, i[:, :nv].clamp_min(0))
         torch.testing.assert_close(got, s[:, :nv], rtol=1e-3, atol=1e-3)   # every returned id really has that score
     cases += 1
-    if cases % 20 == 0:   # MaxSim, both families, ragged documents
-        nqm, lq = int(rng.choice([1, 8, 40])), int(rng.choice([32, 20]))
+    if cases % 10 == 0:   # MaxSim: shared candidates (both tcgen05 kernels by shape), per-query candidates, mma.sync
+        nqm, lq = int(rng.choice([1, 3, 8, 40])), int(rng.choice([32, 20, 70]))
         lens = rng.integers(1, 400, size=int(rng.integers(1, 60))).tolist()
         qe = torch.randn(nqm, lq, 128, generator=g, device=dev).bfloat16()
         docs = [torch.randn(L, 128, generator=g, device=dev).bfloat16() for L in lens]
@@ -52,6 +52,13 @@ while time.time() - t0 < budget:
         w = torch.ones(lq, device=dev); w[0] = 0; w[-1] = 0
         want = torch.stack([((qe.float() @ dd.float().T).max(dim=2).values * w).sum(dim=1) for dd in docs], dim=1)
         torch.testing.assert_close(out, want, rtol=2e-3, atol=2e-2)
-        launches += 1
+        nc = int(rng.integers(1, len(lens) + 1))
+        cand = torch.from_numpy(rng.integers(0, len(lens), size=(nqm, nc)).astype(np.int32)).to(dev)
+        for impl in (_ffi.RS_MAXSIM_TCGEN05_CAND, _ffi.RS_MAXSIM_MMA):
+            eng.set_maxsim_impl(impl)
+            outc = eng.maxsim(qe, toks, off, cand=cand)
+            eng.set_maxsim_impl(_ffi.RS_MAXSIM_AUTO)
+            torch.testing.assert_close(outc, torch.gather(want, 1, cand.long()), rtol=2e-3, atol=2e-2)
+        launches += 3
 torch.cuda.synchronize()
 print(f"soak ok: {cases} dense cases, ~{launches} launches in {time.time() - t0:.0f} s, engine launch count {eng.launch_count}")
