@@ -26,6 +26,29 @@ from .documents import Document
 logger = logging.getLogger(__name__)
 
 
+# Pinned staging for host-resident embeddings (the reference's CPU call shape): the rows are concatenated straight
+# into page-locked memory and go up in one DMA; a pageable source would be copied once more by the driver.
+_PINNED: Dict[Tuple[int, torch.dtype], Tuple[torch.Tensor, "torch.cuda.Event"]] = {}
+
+
+def _stage_host_rows(mats: Sequence[torch.Tensor], rows: int, device: torch.device) -> torch.Tensor:
+    cols, dt = mats[0].shape[1], mats[0].dtype
+    key = (device.index if device.index is not None else torch.cuda.current_device(), dt)
+    buf, ev = _PINNED.get(key, (None, None))
+    if ev is not None:
+        ev.synchronize()  # the previous upload out of this buffer has finished
+    if buf is None or buf.numel() < rows * cols:
+        buf = torch.empty(max(rows * cols, 1 << 20), dtype=dt).pin_memory()
+    view = buf[: rows * cols].view(rows, cols)
+    torch.cat(list(mats), dim=0, out=view)
+    with torch.cuda.device(device):
+        on_dev = view.to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+    _PINNED[key] = (buf, ev)
+    return on_dev
+
+
 def pack_documents(doc_embeddings_list: Sequence[torch.Tensor], device: torch.device, dtype: torch.dtype
                    ) -> Tuple[torch.Tensor, torch.Tensor]:
     """List of [Ld_i, D] tensors -> (tokens [sum Ld, D] on `device`, offsets int32 [n+1] on `device`)."""
@@ -40,10 +63,14 @@ def pack_documents(doc_embeddings_list: Sequence[torch.Tensor], device: torch.de
             raise ValueError("document with zero tokens")  # torch.max over an empty dim raises in the reference too
         lens.append(d.size(0))
         mats.append(d)
+    device = torch.device(device)
     if len({(m.device, m.dtype) for m in mats}) == 1:
         # one concatenation where the tensors live, then ONE transfer / cast (100 small H2D copies cost more
         # than the scoring kernel itself)
-        tokens = torch.cat(mats, dim=0).to(device=device, dtype=dtype).contiguous()
+        if mats[0].device.type == "cpu" and device.type == "cuda":
+            tokens = _stage_host_rows(mats, sum(lens), device).to(dtype).contiguous()
+        else:
+            tokens = torch.cat(mats, dim=0).to(device=device, dtype=dtype).contiguous()
     else:
         tokens = torch.cat([m.to(device=device, dtype=dtype) for m in mats], dim=0).contiguous()
     offs = torch.zeros(len(lens) + 1, dtype=torch.int64)
