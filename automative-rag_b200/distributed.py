@@ -131,3 +131,50 @@ class ShardedMaxSim:
             lo, hi = shard_bounds(self.nd_total, self.world, r)
             cols.append(blocks[r, :, : hi - lo])
         return torch.cat(cols, dim=1)
+
+
+def partition_candidates(cand: torch.Tensor, world_size: int, rank: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-query candidate lists `cand` [nq, nc] of GLOBAL document ids, documents owned round-robin
+    (owner = id % world_size, local index = id // world_size).  Returns
+      slots     int64 [nq, width]  positions in `cand` of the candidates this rank owns, owned ones first
+                                   (original order kept), width = the widest owned count of any query
+      loc_cand  int32 [nq, width]  local document indices for `rs_maxsim`, -1 where a query owns fewer than
+                                   `width` (an index outside the collection is an empty document: score -inf).
+    """
+    mine = (cand % world_size) == rank
+    order = torch.argsort((~mine).to(torch.int8), dim=1, stable=True)
+    width = int(mine.sum(dim=1).max().item()) if cand.numel() else 0
+    slots = order[:, :width]
+    owned = torch.gather(mine, 1, slots)
+    loc = torch.div(torch.gather(cand, 1, slots), world_size, rounding_mode="floor")
+    loc_cand = torch.where(owned, loc, torch.full_like(loc, -1)).to(torch.int32).contiguous()
+    return slots, loc_cand
+
+
+class ShardedCandidateMaxSim:
+    """Retrieve-then-rerank shape (BASELINE config 4b / stage 2 of config 5): every query has its own candidate
+    list; a candidate's token embeddings live on the rank that owns the document (id % G).  Each rank scores the
+    candidates it owns, ONE all-gather of the [nq, nc] score blocks, element-wise max (every candidate has exactly
+    one owner, all other ranks contribute -inf)."""
+
+    def __init__(self, local_tokens: torch.Tensor, local_offsets: torch.Tensor, *, engine=None, group=None,
+                 local_score: Optional[Callable] = None):
+        self.tokens, self.offsets = local_tokens, local_offsets
+        self.engine, self.group = engine, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._local_score = local_score or (
+            lambda q, loc_cand, w: self.engine.maxsim(q, self.tokens, self.offsets, q_weight=w, cand=loc_cand))
+
+    def scores(self, q: torch.Tensor, cand: torch.Tensor, q_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[nq, nc] fp32 on every rank, column j = score of cand[:, j]."""
+        nq, nc = cand.shape
+        slots, loc_cand = partition_candidates(cand, self.world, self.rank)
+        full = torch.full((nq, nc), float("-inf"), dtype=torch.float32, device=cand.device)
+        if slots.shape[1]:
+            full.scatter_(1, slots, self._local_score(q, loc_cand, q_weight))
+        if self.world == 1:
+            return full
+        out = torch.empty(self.world * nq * nc, dtype=torch.float32, device=cand.device)
+        dist.all_gather_into_tensor(out, full.reshape(-1), group=self.group)
+        return out.view(self.world, nq, nc).max(dim=0).values

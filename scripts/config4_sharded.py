@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
 import automative_rag_b200 as rag
-from automative_rag_b200.distributed import ShardedMaxSim, shard_bounds
+from automative_rag_b200.distributed import ShardedCandidateMaxSim, ShardedMaxSim, shard_bounds
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -62,22 +62,12 @@ cand = torch.randint(0, pool, (nq, nc), generator=torch.Generator(device=dev).ma
 own = torch.arange(rank, pool, world, device=dev)                      # documents this rank owns
 loc_pool = ptoks.view(pool, ld * d)[own].reshape(-1, d).contiguous()
 loc_poff = (torch.arange(own.numel() + 1, dtype=torch.int32) * ld).to(dev)
+cand_sharded = ShardedCandidateMaxSim(loc_pool, loc_poff, engine=eng)
+
+
 def step_b():
-    # partition of the step's candidate lists (part of the step): this rank's candidates first, padded with -1
-    # (an index outside the collection is an empty document: no reads, score -inf)
-    mine = (cand % world) == rank
-    order = torch.argsort((~mine).to(torch.int8), dim=1, stable=True)            # owned slots first, original order kept
-    width = int(mine.sum(dim=1).max().item()) if world > 1 else nc                # one host sync per step
-    slots = order[:, :width]
-    loc_cand = torch.where(torch.gather(mine, 1, slots), torch.gather(cand, 1, slots) // world,
-                           torch.full_like(slots, -1, dtype=torch.int32)).to(torch.int32).contiguous()
-    sc_loc = eng.maxsim(q, loc_pool, loc_poff, cand=loc_cand)                     # [nq, width]
-    sc = torch.full((nq, nc), float("-inf"), device=dev).scatter_(1, slots, sc_loc)
-    if world == 1:
-        return sc
-    out = torch.empty(world, nq, nc, dtype=torch.float32, device=dev)
-    dist.all_gather_into_tensor(out, sc)
-    return out.max(dim=0).values
+    # the partition of the step's candidate lists (owned candidates first, -1 padding) is part of the step
+    return cand_sharded.scores(q, cand)
 
 
 ms_b = timed(step_b, iters=10)

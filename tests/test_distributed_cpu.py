@@ -53,6 +53,26 @@ def _worker(rank, world, port, n, d, k, nq, out_dir):
         sm = ShardedMaxSim(None, None, nd, local_score=lambda q, w: full[:, dlo:dhi].clone())
         got = sm.scores(queries)
         np.save(os.path.join(out_dir, f"maxsim_{rank}.npy"), got.numpy())
+
+        # per-query candidate lists: documents owned round-robin, each rank scores what it owns
+        from automative_rag_b200.distributed import ShardedCandidateMaxSim
+
+        pool, nc = 23, 9
+        gc = torch.Generator().manual_seed(3)
+        cand = torch.stack([torch.randperm(pool, generator=gc)[:nc] for _ in range(nq)]).to(torch.int32)
+        doc_score = torch.arange(pool, dtype=torch.float32) * 1.5 + 0.25          # stand-in for MaxSim(q, doc)
+        own = torch.arange(rank, pool, world)                                      # global ids this rank owns
+
+        def local_score(q, loc_cand, w):
+            loc = loc_cand.long()
+            glob = own[loc.clamp_min(0).clamp_max(len(own) - 1)]
+            out = doc_score[glob] + torch.arange(q.shape[0], dtype=torch.float32)[:, None]
+            return torch.where(loc >= 0, out, torch.full_like(out, float("-inf")))
+
+        sc = ShardedCandidateMaxSim(None, None, local_score=local_score).scores(queries, cand)
+        np.save(os.path.join(out_dir, f"cand_{rank}.npy"), sc.numpy())
+        np.save(os.path.join(out_dir, f"cand_want_{rank}.npy"),
+                (doc_score[cand.long()] + torch.arange(nq, dtype=torch.float32)[:, None]).numpy())
     finally:
         dist.destroy_process_group()
 
@@ -75,3 +95,23 @@ def test_sharded_dense_search_two_ranks_gloo(tmp_path):
     full = np.arange(nq * 7, dtype=np.float32).reshape(nq, 7)
     for r in range(world):
         np.testing.assert_array_equal(np.load(tmp_path / f"maxsim_{r}.npy"), full)
+        # per-query candidates: every rank ends with the score of every candidate, in the caller's order
+        np.testing.assert_array_equal(np.load(tmp_path / f"cand_{r}.npy"), np.load(tmp_path / f"cand_want_{r}.npy"))
+
+
+def test_partition_candidates_single_process():
+    from automative_rag_b200.distributed import partition_candidates
+
+    cand = torch.tensor([[5, 8, 2, 11, 4], [1, 3, 7, 9, 13], [0, 2, 4, 6, 8]], dtype=torch.int32)
+    seen = torch.zeros_like(cand, dtype=torch.int32)
+    for rank in range(3):
+        slots, loc = partition_candidates(cand, 3, rank)
+        assert slots.shape == loc.shape and loc.dtype == torch.int32
+        for q in range(cand.shape[0]):
+            owned = [(j, int(c)) for j, c in enumerate(cand[q].tolist()) if c % 3 == rank]
+            n_owned = len(owned)
+            assert slots[q, :n_owned].tolist() == [j for j, _ in owned]            # owned first, original order
+            assert loc[q, :n_owned].tolist() == [c // 3 for _, c in owned]         # local index of a round-robin owner
+            assert (loc[q, n_owned:] == -1).all()                                  # padding = empty document
+            seen[q, slots[q, :n_owned]] += 1
+    assert (seen == 1).all()                                                       # every candidate has one owner
