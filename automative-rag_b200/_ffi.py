@@ -32,6 +32,7 @@ SIGNATURES = {
     "rs_set_dense_impl": (C.c_int, [_P, C.c_int]),
     "rs_set_maxsim_impl": (C.c_int, [_P, C.c_int]),
     "rs_set_scan_trace": (C.c_int, [_P, _P]),
+    "rs_scan_plan": (C.c_int, [_I32, _I32, C.POINTER(_I64)]),
     "rs_last_dense_impl": (C.c_int, [_P]),
     "rs_last_maxsim_impl": (C.c_int, [_P]),
     "rs_dense_topk": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _I32, _P, _I64, _I32, _I64, _P, _P, _P]),

@@ -607,6 +607,17 @@ static ScanPlan scan_plan(int d, int k) {
 
 int scan_stages(int d, int k) { return scan_plan(d, k).stages; }
 
+void scan_plan_query(int d, int k, int64_t out[7]) {
+  const ScanPlan pl = scan_plan(d, k);
+  out[0] = pl.tile_rows;
+  out[1] = pl.consumers;
+  out[2] = pl.stages;
+  out[3] = pl.buf_cap;
+  out[4] = pl.buf_hw;
+  out[5] = pl.rounds_per_check;
+  out[6] = (int64_t)pl.smem;
+}
+
 size_t scan_smem_bytes(int d, int k) { return scan_plan(d, k).smem; }
 
 // Smallest grab, in mask words: at least 64 KB of rows, so that the counter's round trip (~1 us)

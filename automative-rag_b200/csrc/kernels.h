@@ -35,6 +35,9 @@ struct ScanParams {
 };
 int scan_tile_rows(int d);
 size_t scan_smem_bytes(int d, int k);
+// shared-memory plan of a scan launch: out[0..6] = tile_rows, consumers, stages, buf_cap, buf_hw, rounds_per_check,
+// dynamic shared-memory bytes (host-only arithmetic; exported through rs_scan_plan for the CPU tests)
+void scan_plan_query(int d, int k, int64_t out[7]);
 // pdl: launch with programmatic stream serialization (only between consecutive scans of one call,
 // whose inputs are all complete before the first launch; see dense_scan.cu)
 cudaError_t launch_dense_scan(ScanParams p, int dtype, int num_sms, bool pdl, cudaStream_t stream);

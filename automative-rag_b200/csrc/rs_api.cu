@@ -188,6 +188,11 @@ int rs_set_scan_trace(rs_handle* h, uint64_t* trace_dev) {
   h->scan_trace = trace_dev;
   return RS_OK;
 }
+int rs_scan_plan(int32_t d, int32_t k, int64_t* out7) {
+  if (!out7 || d <= 0 || (d % 8) != 0 || d > 4096 || k < 1 || k > kMaxK) return RS_ERR_INVALID_ARG;
+  rs::scan_plan_query(d, k, out7);
+  return RS_OK;
+}
 int rs_last_dense_impl(const rs_handle* h) { return h ? h->last_dense_impl : 0; }
 int rs_last_maxsim_impl(const rs_handle* h) { return h ? h->last_maxsim_impl : 0; }
 

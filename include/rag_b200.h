@@ -104,6 +104,13 @@ int rs_set_maxsim_impl(rs_handle* h, int impl);
  * done); launch i writes block (i mod 8).  Used by scripts/scan_trace.py; off by default.
  */
 int rs_set_scan_trace(rs_handle* h, uint64_t* trace_dev);
+/*
+ * Diagnostics, no device needed: the shared-memory plan the single-query scan uses for row length d and list length
+ * k — out7 = { rows per tile, consumer warps, ring slots, top-k buffer capacity, its high-water mark, consumer
+ * rounds between two buffer checks, dynamic shared-memory bytes }.  tests/test_abi.py checks its invariants for every
+ * supported (d, k) on CPU.
+ */
+int rs_scan_plan(int32_t d, int32_t k, int64_t* out7);
 /* Family used by the most recent rs_dense_topk / rs_maxsim call on this handle. */
 int rs_last_dense_impl(const rs_handle* h);
 int rs_last_maxsim_impl(const rs_handle* h);

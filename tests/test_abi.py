@@ -42,6 +42,30 @@ def test_header_enums_match_the_python_constants():
         assert getattr(_ffi, name) == value, f"{name}: header {value}, _ffi.py {getattr(_ffi, name)}"
 
 
+def test_scan_shared_memory_plan_invariants():
+    """Host-side sizing of the scan for every supported row length and a spread of k: the top-k buffer can never
+    overflow between two checks, a compaction always gets below the high-water mark, every ring slot has exactly one
+    owning consumer warp (one or two slots each), and everything fits the 227 KB a CTA may use."""
+    lib = rag.load_library()
+    out = (ctypes.c_int64 * 7)()
+    ks = [1, 2, 10, 31, 32, 33, 100, 128, 129, 500, 1000, 1024, 1025, 1365, 1366, 2000, 2048]
+    for d in range(8, 4097, 8):
+        for k in ks:
+            assert lib.rs_scan_plan(d, k, out) == 0
+            tile_rows, consumers, stages, cap, hw, rounds, smem = list(out)
+            assert 1 <= tile_rows <= 32 and tile_rows & (tile_rows - 1) == 0
+            assert tile_rows * d * 2 <= 8192 or tile_rows == 1
+            assert 2 <= consumers <= 13 and stages in (consumers, 2 * consumers)
+            assert cap & (cap - 1) == 0 and cap >= 512
+            slack = cap - hw
+            assert slack >= consumers * tile_rows * rounds            # appends between two checks fit above high water
+            assert slack >= 1 and hw >= k + k // 2 >= k               # a compaction (k survivors) frees >= k / 2 slots
+            assert rounds >= 1
+            ring = stages * tile_rows * d * 2
+            assert smem >= ring + cap * 8 and smem <= 227 * 1024
+    assert lib.rs_scan_plan(12, 10, out) != 0 and lib.rs_scan_plan(1024, 0, out) != 0 and lib.rs_scan_plan(1024, 4096, out) != 0
+
+
 def test_library_loads_and_reports_abi_version():
     lib = rag.load_library()
     assert lib.rs_abi_version() == 1
