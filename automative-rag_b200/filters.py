@@ -7,7 +7,7 @@ that inspect `filter.must[0].key`, `.match.value`, `.range.gte`, `.should` read 
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
 
 

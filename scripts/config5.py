@@ -12,7 +12,7 @@
         scripts/config5.py --rows-per-gpu 12500000 --pool-docs 1000000 --queries 20
   --check  small sizes + comparison with a single-process CPU oracle on rank 0
 """
-import argparse, json, os, sys, time
+import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch

@@ -6,7 +6,6 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import automative_rag_b200 as rag
-from automative_rag_b200 import _ffi
 eng = rag.get_engine(0); dev = eng.device
 d, k = 1024, 10
 g = torch.Generator(device=dev).manual_seed(1)

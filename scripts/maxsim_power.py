@@ -1,6 +1,6 @@
 """Is MaxSim config 4a power/clock bound?  (a) isolated launches with idle gaps, (b) a 2 s back-to-back loop with
 nvidia-smi clock / power sampling."""
-import os, sys, time, subprocess, statistics
+import os, sys, time, subprocess
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import automative_rag_b200 as rag
