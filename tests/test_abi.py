@@ -116,3 +116,43 @@ def test_header_is_plain_c_and_the_c_client_links(tmp_path):
         return  # the device part is exercised on the GPU box (profiles/r01_c_client.txt)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "ABI version 1" in r.stdout and "no CPU fallback" in r.stdout
+
+
+def test_sass_of_the_hot_kernels_uses_the_blackwell_units():
+    """The shipped library is sm_100a code that really uses TMA bulk copies, TMA tensor loads, tcgen05 MMAs (single-CTA
+    and CTA-pair), TMEM loads and the mixed-precision FMA — per kernel, from `cuobjdump -sass` (no GPU needed)."""
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("no cuobjdump")
+    out = subprocess.run([cuobjdump, "-sass", _ffi.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    assert "sm_100a" in out
+    per_kernel = {}
+    name = None
+    for line in out.splitlines():
+        if "Function :" in line:
+            name = line.split("Function :")[1].strip()
+            per_kernel[name] = []
+        elif name is not None:
+            per_kernel[name].append(line)
+
+    def kernels(fragment):
+        hits = {k: "\n".join(v) for k, v in per_kernel.items() if fragment in k}
+        assert hits, f"no kernel named *{fragment}* in the library"
+        return hits
+
+    for k, sass in kernels("dense_scan_kernel").items():
+        assert "UBLKCP" in sass and "FHFMA" in sass and "SYNCS" in sass, k      # TMA bulk copy, 16-bit x 16-bit -> fp32 FMA
+    for k, sass in kernels("maxsim_tc5_kernel").items():
+        assert "UTMALDG" in sass and "UTCHMMA" in sass and "LDTM" in sass, k     # TMA tensor load, tcgen05.mma, tcgen05.ld
+    for k, sass in kernels("maxsim_cand_tc5_kernel").items():
+        assert "UTMALDG" in sass and "UTCHMMA" in sass and "LDTM" in sass, k
+    pair = [s for k, s in kernels("dense_tc5_kernel").items() if "UTCHMMA.2CTA" in s]
+    single = [s for k, s in kernels("dense_tc5_kernel").items() if "UTCHMMA.2CTA" not in s]
+    assert len(pair) == 2 and len(single) == 2                                   # fp16 / bf16 x pair / single-CTA
+    for sass in pair:
+        assert "UTMALDG.2D.2CTA" in sass and "UTCBAR.2CTA.MULTICAST" in sass and "UCGABAR" in sass
+    for k, sass in kernels("maxsim_mma_kernel").items():
+        assert "HMMA.16816" in sass, k                                           # the legacy mma.sync fallback
