@@ -196,7 +196,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "config2", "rows": args.rows, "dim": DIM, "k": args.k, "mask_p": args.mask_p,
-                   "queries_per_step": per_step},
+                   "queries_per_step": args.queries_per_step, "sampled_queries_per_step": per_step},
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{per_step} full-corpus queries per step x {args.steps} steps (numpy restatement "
                                    "of qdrant-client local mode; fp16 corpus upcast to fp32 once, untimed)"},
