@@ -165,6 +165,7 @@ def test_hybrid_retriever_composition(store):
                                  query_encoder=lambda t: torch.randn(1, 32, 64, generator=torch.Generator().manual_seed(1)),
                                  doc_encoder=lambda texts: [table[t] for t in texts])
     hr = rag.HybridRetriever(store, rr, top_k=20, rerank_top_k=5)
-    out = hr.retrieve("q", metadata_filter={"manufacturer": "Honda"})
+    out, seconds = hr.retrieve("q", metadata_filter={"manufacturer": "Honda"})
+    assert seconds > 0
     assert len(out) == 5 and all(d.metadata["manufacturer"] == "Honda" for d, _ in out)
     assert [s for _, s in out] == sorted([s for _, s in out], reverse=True)

@@ -46,3 +46,47 @@ def test_pack_documents():
     assert off.tolist() == [0, 3, 8, 10] and off.dtype == torch.int32
     with pytest.raises(ValueError):
         pack_documents([torch.randn(0, 8)], torch.device("cpu"), torch.float16)
+
+
+def test_hybrid_retriever_matches_the_reference_tests():
+    """The reference's own expectations for HybridRetriever (tests/test_retrieval.py:191-276), with stand-ins for the
+    store and the reranker exactly as the reference mocks them: argument forwarding, (results, execution_time), the
+    rerank_top_k cut without reranking — plus the per-mode sizes of mode_config.py."""
+    from unittest.mock import MagicMock
+
+    from automative_rag_b200.documents import Document
+    from automative_rag_b200.retriever import HybridRetriever, retrieval_params
+
+    store, reranker = MagicMock(), MagicMock()
+    r = HybridRetriever(vector_store=store, reranker=reranker, top_k=20, rerank_top_k=5)
+    assert r.vector_store is store and r.reranker is reranker and r.top_k == 20 and r.rerank_top_k == 5
+
+    r = HybridRetriever(vector_store=store, reranker=reranker, top_k=10, rerank_top_k=3)
+    documents = [(Document(page_content=f"Doc {i}", metadata={"id": str(i)}), 1.0 - 0.1 * i) for i in (1, 2, 3, 4)]
+    reranked = [documents[2], documents[0], documents[1]]
+    store.similarity_search_with_score.return_value = documents
+    reranker.rerank.return_value = reranked
+    results, seconds = r.retrieve(query="What is the horsepower?", metadata_filter={"manufacturer": "Toyota"}, rerank=True)
+    assert results == reranked and seconds > 0
+    store.similarity_search_with_score.assert_called_once_with(query="What is the horsepower?", k=10,
+                                                               metadata_filter={"manufacturer": "Toyota"})
+    reranker.rerank.assert_called_once_with(query="What is the horsepower?", documents=[d for d, _ in documents], top_k=3)
+
+    store.reset_mock(), reranker.reset_mock()
+    store.similarity_search_with_score.return_value = documents
+    results, seconds = r.retrieve(query="What is the horsepower?", metadata_filter={"manufacturer": "Toyota"}, rerank=False)
+    assert results == documents[:3] and seconds > 0
+    store.similarity_search_with_score.assert_called_once()
+    reranker.rerank.assert_not_called()
+
+    # per-mode sizes (mode_config.py): retrieval_k for the search, final_k after reranking; unknown -> facts
+    assert retrieval_params("debate") == (40, 18) and retrieval_params("FACTS") == (20, 8) and retrieval_params("nope") == (20, 8)
+    store.reset_mock(), reranker.reset_mock()
+    store.similarity_search_with_score.return_value = documents
+    r.retrieve(query="q", mode="tradeoffs")
+    assert store.similarity_search_with_score.call_args.kwargs["k"] == 35
+    assert reranker.rerank.call_args.kwargs["top_k"] == 15
+
+    store.similarity_search_with_score.return_value = []
+    results, seconds = r.retrieve(query="q")
+    assert results == [] and seconds > 0
