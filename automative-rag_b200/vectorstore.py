@@ -5,7 +5,7 @@ Mirrors src/core/query/retrieval/vectorstore.py of the reference: same construct
 same `similarity_search_with_score(query, k=5, metadata_filter=None)` (:166-214) including the
 "filtered search failed -> log and retry unfiltered" behaviour (:199-207), same `_build_filter`
 (:216-276), `add_documents` (:124-164), `search_by_metadata` (:278-316), `delete_by_ids`
-(:318-353) and `get_stats` (:355-388).
+(:318-353), `get_stats` (:355-388), `get_embedding` (:390-411) and `repair_indices` (:412-470).
 
 What changes is what sits underneath.  The reference forwards to a Qdrant server; here the
 collection lives in one GPU's HBM:
@@ -127,6 +127,21 @@ class Collection:
         self.ids.extend(ids)
         self.payloads.extend(payloads)
         self.n += m
+
+    def rebuild_columns(self) -> List[str]:
+        """Re-encode every stored payload into fresh payload columns and keyword dictionaries — the counterpart of
+        dropping and recreating Qdrant's payload indexes (vectorstore.py:412-470).  Returns the rebuilt fields."""
+        self.keyword_dicts = {f: {} for f in KEYWORD_FIELDS}
+        cols: Dict[str, List[int]] = {f: [] for f in self.columns}
+        for p in self.payloads:
+            for f, val in self._encode_fields(p.get("metadata", {}) or {}).items():
+                cols[f].append(val)
+        for f, vals in cols.items():
+            col = torch.full((self.capacity,), INT_MISSING, dtype=torch.int32, device=self.device)
+            if vals:
+                col[: self.n] = torch.tensor(vals, dtype=torch.int32, device=self.device)
+            self.columns[f] = col
+        return list(self.columns)
 
     def delete(self, ids: Sequence[str]) -> int:
         """Tombstone the rows of `ids` (unknown ids are ignored, as Qdrant does)."""
@@ -378,6 +393,21 @@ class B200VectorStore:
         except Exception as e:
             logger.error(f"Error getting collection stats: {str(e)}")
             return {"name": self.collection_name, "error": str(e)}
+
+    # vectorstore.py:412-470
+    def repair_indices(self) -> Dict[str, Any]:
+        """Rebuild the payload columns from the stored payloads; same result shape as the reference."""
+        logger.info(f"Attempting to repair indices for collection '{self.collection_name}'")
+        results: Dict[str, Any] = {"recreated_indices": [], "errors": [], "success": False}
+        try:
+            results["recreated_indices"] = [f"metadata.{f}" for f in self.collection.rebuild_columns()]
+            results["success"] = True
+            logger.info("Repair completed successfully")
+        except Exception as e:
+            error_msg = f"Error during repair: {str(e)}"
+            logger.error(error_msg)
+            results["errors"].append(error_msg)
+        return results
 
     # vectorstore.py:390-411
     def get_embedding(self, id: str) -> Optional[List[float]]:

@@ -90,3 +90,44 @@ def test_hybrid_retriever_matches_the_reference_tests():
     store.similarity_search_with_score.return_value = []
     results, seconds = r.retrieve(query="q")
     assert results == [] and seconds > 0
+
+
+def test_collection_storage_logic_on_cpu_tensors():
+    """The store's host-side bookkeeping (row storage, dictionary-encoded payload columns, tombstones, upsert-replaces,
+    rebuild of the columns) does not depend on the GPU: run it over CPU tensors with a stand-in for the engine (whose
+    only job here would be rs_filter_mask / rs_dense_topk, not exercised)."""
+    from types import SimpleNamespace
+
+    from automative_rag_b200.filters import INT_MISSING
+    from automative_rag_b200.vectorstore import INTEGER_FIELDS, KEYWORD_FIELDS, Collection
+
+    col = Collection("c", 16, SimpleNamespace(device=torch.device("cpu")), capacity=4)
+    g = torch.Generator().manual_seed(0)
+    vec = torch.randn(6, 16, generator=g)
+    pay = [{"page_content": f"t{i}", "metadata": {"manufacturer": ["Toyota", "Honda"][i % 2], "year": 2020 + i,
+                                                  "model": None, "ingestion_time": True}} for i in range(6)]
+    col.upsert([f"id{i}" for i in range(6)], vec, pay)
+    assert col.n == 6 and col.capacity >= 6 and col.capacity % 32 == 0
+    stored = col.vectors[:6].float()
+    np.testing.assert_allclose(stored.norm(dim=1).numpy(), 1.0, atol=2e-3)                 # unit rows (Distance.COSINE)
+    np.testing.assert_allclose((col.inv_norm[:6] * stored.norm(dim=1)).numpy(), 1.0, atol=1e-6)
+    assert col.columns["manufacturer"][:6].tolist() == [0, 1, 0, 1, 0, 1]                  # dictionary codes
+    assert col.columns["year"][:6].tolist() == [2020, 2021, 2022, 2023, 2024, 2025]
+    assert col.columns["model"][:6].tolist() == [-1] * 6                                   # absent keyword
+    assert col.columns["ingestion_time"][:6].tolist() == [INT_MISSING] * 6                 # a bool is not an integer
+    assert set(col.columns) == set(KEYWORD_FIELDS + INTEGER_FIELDS)
+
+    assert col.delete(["id1", "nope", "id4"]) == 2 and col.deleted == 2
+    assert col.tombstone[0].item() == (1 << 1) | (1 << 4)
+    assert "id1" not in col.id_to_row and col.id_to_row["id5"] == 5
+
+    col.upsert(["id0"], torch.randn(1, 16, generator=g), [{"page_content": "new", "metadata": {"manufacturer": "Kia"}}])
+    assert col.n == 7 and col.id_to_row["id0"] == 6 and col.deleted == 3                   # upsert replaces the point
+    assert col.columns["manufacturer"][6].item() == 2 and col.keyword_dicts["manufacturer"]["Kia"] == 2
+
+    before = {f: col.columns[f][: col.n].clone() for f in col.columns}
+    col.columns["year"][: col.n] = 0                                                       # damage an "index"
+    assert sorted(col.rebuild_columns()) == sorted(KEYWORD_FIELDS + INTEGER_FIELDS)
+    for f in col.columns:
+        assert torch.equal(col.columns[f][: col.n], before[f]), f                          # ... and it is restored
+        assert (col.columns[f][col.n:] == INT_MISSING).all()
