@@ -72,3 +72,75 @@ def make_dense_case(seed: int, n: int, d: int, dtype: torch.dtype = torch.float1
 def bernoulli_mask(seed: int, n: int, p: float) -> np.ndarray:
     """bool [n], True = row passes, Bernoulli(p)."""
     return np.random.default_rng(seed).random(n) < p
+
+
+# ---------------------------------------------------------------------------------- explanations
+class StubTokenizer:
+    """Whitespace word-piece look-alike with BERT's interface subset the explanations path uses
+    (rerankers.py:432-443, :460-473, :503): [CLS] w1 w2 ... [SEP] [PAD]...; words longer than 6 characters are split
+    into a head and a '##' continuation so the wordpiece branches run."""
+
+    def __init__(self):
+        self.vocab = ["[PAD]", "[CLS]", "[SEP]", "[UNK]"]
+        self.index = {t: i for i, t in enumerate(self.vocab)}
+
+    def _pieces(self, text):
+        out = []
+        for w in text.lower().split():
+            out.extend([w[:6], "##" + w[6:]] if len(w) > 6 else [w])
+        return out
+
+    def _id(self, tok):
+        if tok not in self.index:
+            self.index[tok] = len(self.vocab)
+            self.vocab.append(tok)
+        return self.index[tok]
+
+    def __call__(self, texts, add_special_tokens=True, max_length=32, padding="max_length", truncation=True,
+                 return_tensors="pt"):
+        from types import SimpleNamespace
+
+        ids, masks = [], []
+        for t in texts:
+            toks = ["[CLS]"] + self._pieces(t)[: max_length - 2] + ["[SEP]"]
+            row = [self._id(x) for x in toks]
+            masks.append([1] * len(row) + [0] * (max_length - len(row)))
+            ids.append(row + [0] * (max_length - len(row)))
+        return SimpleNamespace(input_ids=torch.tensor(ids), attention_mask=torch.tensor(masks))
+
+    def convert_ids_to_tokens(self, ids):
+        return [self.vocab[i] for i in ids]
+
+
+EXPLAIN_CASE = dict(
+    seed=31, d=64, max_query_length=16, max_doc_length=24, num_explanations=4,
+    query="which engine has the strongest horsepower rating",
+    docs=["the turbocharged engine delivers impressive horsepower figures on track",
+          "comfortable seats and a quiet cabin make long trips pleasant",
+          "horsepower rating of the strongest variant exceeds expectations easily"],
+)
+
+
+def make_explain_case(spec: dict = EXPLAIN_CASE):
+    """Token embeddings with unambiguous matches: every distinct word piece gets a random unit vector, a token's
+    embedding is its piece's vector plus small position noise, specials / padding get their own vectors — so a query
+    token's best document token is the same piece when the document has it (margin ~1 vs ~0.1), also in fp16."""
+    tok = StubTokenizer()
+    g = torch.Generator().manual_seed(spec["seed"])
+    table = {}
+
+    def vec(piece):
+        if piece not in table:
+            v = torch.randn(spec["d"], generator=g)
+            table[piece] = v / v.norm()
+        return table[piece]
+
+    def embed(text, max_length):
+        enc = tok([text], max_length=max_length)
+        pieces = tok.convert_ids_to_tokens(enc.input_ids[0].tolist())
+        rows = [vec(p) + 0.02 * torch.randn(spec["d"], generator=g) for p in pieces]
+        return torch.stack(rows)
+
+    q = embed(spec["query"], spec["max_query_length"]).unsqueeze(0)              # [1, Lq, d]
+    docs = {t: embed(t, spec["max_doc_length"]) for t in spec["docs"]}           # text -> [Ld, d]
+    return tok, q, docs

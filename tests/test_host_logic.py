@@ -131,3 +131,45 @@ def test_collection_storage_logic_on_cpu_tensors():
     for f in col.columns:
         assert torch.equal(col.columns[f][: col.n], before[f]), f                          # ... and it is restored
         assert (col.columns[f][col.n:] == INT_MISSING).all()
+
+
+def test_explanations_logic_matches_the_reference_golden():
+    """B200ColBERTReranker._explain_colbert_matches (token strings, contexts, per-token similarities, mask-based score
+    rule, ordering) against the output of the reference's own function (tests/golden/explain_golden.json, made by
+    make_golden.py).  The device call is replaced by a stand-in backed by the CPU oracle: what is under test is the
+    host logic around rs_maxsim(out_argmax, q_weight); the kernel's argmax / weights are covered by test_maxsim_gpu."""
+    import json
+    import os
+    from types import SimpleNamespace
+
+    from automative_rag_b200.documents import Document
+    from automative_rag_b200.rerankers import B200ColBERTReranker
+    from oracle import maxsim as omaxsim
+    from tests._cases import EXPLAIN_CASE, make_explain_case
+
+    tok, q_emb, doc_embs = make_explain_case()
+
+    def fake_maxsim(q, tokens, offs, q_weight=None, cand=None, want_argmax=False):
+        off = offs.tolist()
+        docs = [tokens[off[i]: off[i + 1]] for i in range(len(off) - 1)]
+        w = None if q_weight is None else q_weight[0]
+        sc, arg = omaxsim.maxsim_scores(q[0], docs, weights=None if w is None else w.numpy(), return_argmax=True)
+        out = torch.from_numpy(np.asarray(sc, dtype=np.float32)[None].copy())
+        return (out, torch.tensor(np.stack(arg)[None], dtype=torch.int32)) if want_argmax else out
+
+    rr = object.__new__(B200ColBERTReranker)          # the constructor needs a B200; only the host logic runs here
+    rr.engine = SimpleNamespace(device=torch.device("cpu"), maxsim=fake_maxsim)
+    rr.tokenizer, rr.compute_dtype, rr.batch_size = tok, torch.float32, 2
+    rr.max_query_length, rr.max_doc_length = EXPLAIN_CASE["max_query_length"], EXPLAIN_CASE["max_doc_length"]
+    rr.query_encoder = lambda query: q_emb
+    rr.doc_encoder = lambda texts: [doc_embs[t] for t in texts]
+    docs = [Document(page_content=t, metadata={"i": i}) for i, t in enumerate(EXPLAIN_CASE["docs"])]
+    got = rr._explain_colbert_matches(EXPLAIN_CASE["query"], docs, EXPLAIN_CASE["num_explanations"])
+    want = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "explain_golden.json")))
+    assert [r["document"].metadata["i"] for r in got] == [w["doc"] for w in want]
+    for r, w in zip(got, want):
+        assert abs(r["score"] - w["score"]) <= 1e-4 * abs(w["score"])
+        assert [(e["query_token"], e["doc_token"], e["context"]) for e in r["explanations"]] == \
+               [(e["query_token"], e["doc_token"], e["context"]) for e in w["explanations"]]
+        np.testing.assert_allclose([e["similarity"] for e in r["explanations"]],
+                                   [e["similarity"] for e in w["explanations"]], rtol=1e-5)
