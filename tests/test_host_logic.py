@@ -173,3 +173,63 @@ def test_explanations_logic_matches_the_reference_golden():
                [(e["query_token"], e["doc_token"], e["context"]) for e in w["explanations"]]
         np.testing.assert_allclose([e["similarity"] for e in r["explanations"]],
                                    [e["similarity"] for e in w["explanations"]], rtol=1e-5)
+
+
+def _oracle_backed_reranker(case, use_bge):
+    """B200ColBERTReranker with the two device calls replaced by the CPU oracle (the constructor needs a B200)."""
+    from types import SimpleNamespace
+
+    from automative_rag_b200.rerankers import B200ColBERTReranker
+    from oracle import maxsim as omaxsim
+
+    def fake_maxsim(q, tokens, offs, q_weight=None, cand=None, want_argmax=False):
+        out = omaxsim.maxsim_scores_packed(q, q_weight, tokens, offs.numpy(), cand)
+        return torch.from_numpy(out)
+
+    def fake_postprocess(scores, other, top_k, w_a=0.8, w_b=0.2):
+        idx, out = [], []
+        for r in range(scores.shape[0]):
+            ranked = omaxsim.hybrid_rerank(scores[r].tolist(), None if other is None else other[r].tolist(), w_a, w_b, top_k)
+            idx.append([i for i, _ in ranked])
+            out.append([v for _, v in ranked])
+        return torch.tensor(idx, dtype=torch.int32), torch.tensor(out, dtype=torch.float32)
+
+    class Bge:
+        def predict(self, pairs):
+            return np.asarray([case["bge"][int(p[1].split("-")[1])] for p in pairs], dtype=np.float32)
+
+    docs_by_text = {f"doc-{i}": t for i, t in enumerate(case["docs"])}
+    rr = object.__new__(B200ColBERTReranker)
+    rr.engine = SimpleNamespace(device=torch.device("cpu"), maxsim=fake_maxsim, rerank_postprocess=fake_postprocess)
+    rr.compute_dtype, rr.batch_size, rr.colbert_weight, rr.bge_weight = torch.float32, 16, 0.8, 0.2
+    rr.use_bge_reranker, rr.bge_reranker = use_bge, (Bge() if use_bge else None)
+    rr.query_encoder = lambda text: case["queries"][int(text.split("-")[1])]
+    rr.doc_encoder = lambda texts: [docs_by_text[t] for t in texts]
+    return rr
+
+
+def test_rerank_host_logic_matches_the_reference_golden_on_cpu():
+    """rerank / batch_rerank_queries host logic (ColBERT-only, hybrid blend on the top 2*top_k, ties, batches) against
+    the reference's own outputs (tests/golden/rerank_golden.json) with the device calls served by the CPU oracle —
+    the CPU twin of test_dropin_gpu.py::test_reranker_dropin_matches_reference_golden."""
+    import json
+    import os
+
+    from automative_rag_b200.documents import Document
+    from tests._cases import RERANK_CASES, make_rerank_case
+
+    gold_all = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "rerank_golden.json")))
+    for name, spec in RERANK_CASES.items():
+        case, gold = make_rerank_case(spec), gold_all[name]
+        rr = _oracle_backed_reranker(case, spec["use_bge"])
+        docs = [Document(page_content=f"doc-{i}", metadata={"i": i}) for i in range(spec["n_docs"])]
+        res = rr.rerank("q-0", docs, spec["top_k"])
+        assert [d.metadata["i"] for d, _ in res] == [i for i, _ in gold["rerank"]], name
+        np.testing.assert_allclose([s for _, s in res], [s for _, s in gold["rerank"]], rtol=2e-5, atol=1e-4)
+        if spec.get("batch"):
+            b = rr.batch_rerank_queries([f"q-{i}" for i in range(spec["n_queries"])], docs, spec["top_k"])
+            assert list(b) == list(gold["batch"])
+            for key, want in gold["batch"].items():
+                assert [d.metadata["i"] for d, _ in b[key]] == [i for i, _ in want], (name, key)
+                np.testing.assert_allclose([s for _, s in b[key]], [s for _, s in want], rtol=2e-5, atol=1e-4)
+        assert rr.rerank("q-0", []) == [] and rr.batch_rerank_queries([], docs) == {}
