@@ -233,3 +233,102 @@ def test_rerank_host_logic_matches_the_reference_golden_on_cpu():
                 assert [d.metadata["i"] for d, _ in b[key]] == [i for i, _ in want], (name, key)
                 np.testing.assert_allclose([s for _, s in b[key]], [s for _, s in want], rtol=2e-5, atol=1e-4)
         assert rr.rerank("q-0", []) == [] and rr.batch_rerank_queries([], docs) == {}
+
+
+def _oracle_backed_store(dim=64):
+    """B200VectorStore over CPU tensors: the engine's two calls on this path (rs_filter_mask, rs_dense_topk_host) are
+    served by the CPU oracle, so the class's own logic — normalisation on insert, payload columns, tombstones, filter
+    compilation, the retry rule, Document assembly — runs without a GPU."""
+    import zlib
+    from types import SimpleNamespace
+
+    from automative_rag_b200.filters import pack_bits
+    from automative_rag_b200.vectorstore import B200Client, B200VectorStore
+    from oracle import dense as odense
+
+    class FakeEmbeddings:
+        def _vec(self, text):
+            return torch.randn(dim, generator=torch.Generator().manual_seed(zlib.crc32(text.encode()))).tolist()
+
+        def embed_query(self, text):
+            return self._vec(text)
+
+        def embed_documents(self, texts):
+            return [self._vec(t) for t in texts]
+
+    def filter_mask(columns, value_sets, n, tombstone=None, out=None):
+        ok = np.ones(n, dtype=bool)
+        for col, vals in zip(columns, value_sets):
+            ok &= np.isin(col.numpy(), np.asarray(list(vals), dtype=np.int32))
+        words = torch.from_numpy(pack_bits(ok))
+        return words if tombstone is None else words & ~tombstone
+
+    def dense_topk_host(corpus, query, k, mask_dev=None, inv_norm=None, metric=1, **_):
+        n = corpus.shape[0]
+        bits = None
+        if mask_dev is not None:
+            w = mask_dev.numpy().view(np.uint32)
+            bits = ((w[np.arange(n) // 32] >> (np.arange(n) % 32)) & 1).astype(bool)
+        s, i = odense.topk(corpus.numpy(), query.numpy().reshape(-1), k, bits, odense.COSINE,
+                           None if inv_norm is None else inv_norm.numpy())
+        return torch.from_numpy(s)[None], torch.from_numpy(i)[None]
+
+    client = object.__new__(B200Client)
+    client.engine = SimpleNamespace(device=torch.device("cpu"), filter_mask=filter_mask, dense_topk_host=dense_topk_host)
+    client.collections = {}
+    return B200VectorStore(client, "cpu-col", FakeEmbeddings())
+
+
+def test_vector_store_host_logic_on_cpu():
+    from automative_rag_b200.documents import Document
+    from oracle import dense as odense
+    from oracle import filters as ofilters
+
+    store = _oracle_backed_store()
+    makers = ["Toyota", "Honda", "BMW"]
+    docs = [Document(page_content=f"chunk {i} about {makers[i % 3]}",
+                     metadata={"manufacturer": makers[i % 3], "year": 2020 + i % 4, "category": ["sedan", "suv"][i % 2],
+                               "custom": f"c{i % 5}"}) for i in range(300)]
+    ids = store.add_documents(docs)
+    assert len(set(ids)) == 300 and store.get_stats()["vectors_count"] == 300
+    assert all("ingestion_time" in d.metadata and d.metadata["id"] for d in docs)          # vectorstore.py:141-152
+
+    emb = store.embedding_function
+    c = np.asarray(emb.embed_documents([d.page_content for d in docs]), dtype=np.float32)
+    c16 = (c / np.linalg.norm(c, axis=1, keepdims=True)).astype(np.float16)
+    inv = (1.0 / np.linalg.norm(c16.astype(np.float32), axis=1)).astype(np.float32)
+    payloads = [{"page_content": d.page_content, "metadata": d.metadata} for d in docs]
+    for flt in (None, {"manufacturer": "Toyota"}, {"manufacturer": ["Honda", "BMW"], "year": 2021},
+                {"category": "suv", "year": [2020, 2023]}, {"manufacturer": "Nobody"}, {"custom": "c3"}):
+        res = store.similarity_search_with_score("What is the horsepower?", k=7, metadata_filter=flt)
+        q16 = np.asarray(emb.embed_query("What is the horsepower?"), dtype=np.float32).astype(np.float16)
+        ws, wi = odense.topk(c16, q16, 7, ofilters.filter_mask(payloads, flt or {}, None), odense.COSINE, inv)
+        nv = int((wi >= 0).sum())
+        assert [d.page_content for d, _ in res] == [docs[i].page_content for i in wi[:nv]], flt
+        np.testing.assert_allclose([s for _, s in res], ws[:nv], rtol=1e-6)
+        assert all(isinstance(s, float) for _, s in res)
+
+    # delete: tombstoned rows never come back; unknown ids are ignored; stats follow
+    top = store.similarity_search_with_score("query text", k=3)
+    victim = ids[[d.page_content for d in docs].index(top[0][0].page_content)]
+    store.delete_by_ids([victim, "no-such-id"])
+    store.delete_by_ids([])
+    assert store.get_stats()["vectors_count"] == 299
+    again = store.similarity_search_with_score("query text", k=3)
+    assert again[0][0].page_content == top[1][0].page_content
+    assert store.get_embedding(victim) is None and len(store.get_embedding(ids[5])) == 64
+
+    # vectorstore.py:199-207: a filtered search that raises is logged and retried without the filter
+    col = store.collection
+    real = col.device_mask
+    col.device_mask = lambda flt: (_ for _ in ()).throw(RuntimeError("boom")) if flt is not None else real(None)
+    assert len(store.similarity_search_with_score("q", k=5, metadata_filter={"manufacturer": "Toyota"})) == 5
+    col.device_mask = real
+
+    found = store.search_by_metadata({"manufacturer": "BMW", "year": 2021}, limit=5)
+    assert 0 < len(found) <= 5 and all(d.metadata["manufacturer"] == "BMW" and d.metadata["year"] == 2021 for d in found)
+    rep = store.repair_indices()
+    assert rep["success"] and not rep["errors"] and "metadata.manufacturer" in rep["recreated_indices"]
+    assert [d.page_content for d, _ in store.similarity_search_with_score("q", k=4, metadata_filter={"year": 2022})] == \
+           [d.page_content for d, _ in store.similarity_search_with_score("q", k=4, metadata_filter={"year": [2022]})]
+    assert store.add_documents([]) == []
