@@ -115,3 +115,9 @@ def test_partition_candidates_single_process():
             assert (loc[q, n_owned:] == -1).all()                                  # padding = empty document
             seen[q, slots[q, :n_owned]] += 1
     assert (seen == 1).all()                                                       # every candidate has one owner
+    # padding entries (-1: fewer than k results upstream) map to the empty document on whichever rank they land
+    pad = torch.tensor([[4, -1, -1]], dtype=torch.int32)
+    for rank in range(3):
+        slots, loc = partition_candidates(pad, 3, rank)
+        for j, c in zip(slots[0].tolist(), loc[0].tolist()):
+            assert c == (4 // 3 if (pad[0, j] == 4 and rank == 4 % 3) else -1)
