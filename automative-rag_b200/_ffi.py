@@ -15,6 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "librag_b200.so")
 
+ABI_VERSION = 2
 RS_OK, RS_ERR_INVALID_ARG, RS_ERR_UNSUPPORTED, RS_ERR_CUDA, RS_ERR_NO_DEVICE, RS_ERR_NOMEM = 0, -1, -2, -3, -4, -5
 RS_F16, RS_BF16, RS_F32 = 0, 1, 2
 RS_METRIC_IP, RS_METRIC_COSINE = 0, 1
@@ -36,7 +37,7 @@ SIGNATURES = {
     "rs_last_dense_impl": (C.c_int, [_P]),
     "rs_last_maxsim_impl": (C.c_int, [_P]),
     "rs_dense_topk": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _I32, _P, _I64, _I32, _I64, _P, _P, _P]),
-    "rs_dense_topk_host": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _I32, _P, _P, _I64, _I32, _I64, _P, _P]),
+    "rs_dense_topk_host": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _I32, _P, _P, _I64, _I32, _I64, _P, _P, _P]),
     "rs_topk_merge": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I64, _I64, _P, _P, _P]),
     "rs_maxsim": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _I64, _P, _I32, _P, _I32, _P, _P, _P]),
     "rs_rerank_postprocess": (C.c_int, [_P, _P, _P, _I32, _I32, _F, _F, _I32, _P, _P, _P]),
@@ -66,8 +67,8 @@ def load_library() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError here means header and library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.rs_abi_version() != 1:
-        raise EngineError(f"ABI version mismatch: library reports {lib.rs_abi_version()}, binding expects 1")
+    if lib.rs_abi_version() != ABI_VERSION:
+        raise EngineError(f"ABI version mismatch: library reports {lib.rs_abi_version()}, binding expects {ABI_VERSION}")
     _lib = lib
     return lib
 
@@ -227,7 +228,7 @@ class Engine:
             out_ids = torch.empty(nq, k, dtype=torch.int64)
         rc = self._lib.rs_dense_topk_host(self._h, _ptr(corpus), n, d, dtype_code(corpus.dtype), _ptr(inv_norm), metric,
                                           _ptr(queries_host), nq, _ptr(mask_host), _ptr(mask_dev), stride, k, id_base,
-                                          _ptr(out_scores), _ptr(out_ids))
+                                          _ptr(out_scores), _ptr(out_ids), _stream_ptr(self.device))
         self._check(rc, "rs_dense_topk_host")
         return out_scores, out_ids
 

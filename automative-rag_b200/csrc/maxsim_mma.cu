@@ -101,7 +101,17 @@ __global__ void __launch_bounds__(kMmaThreads) maxsim_mma_kernel(const MaxSimPar
     }
   }
 
-  auto doc_of = [&](int slot) { return p.cand ? p.cand[(size_t)qi * p.nc + slot] : slot; };
+  // first token row and length of the document in output slot `slot`; a candidate index outside the collection is
+  // an empty document (score -inf), as in the tcgen05 candidate kernel
+  auto doc_bounds = [&](int slot, int& beg, int& len) {
+    const int dc = p.cand ? p.cand[(size_t)qi * p.nc + slot] : slot;
+    beg = 0;
+    len = 0;
+    if (dc >= 0 && dc < p.nd) {
+      beg = p.doc_offsets[dc];
+      len = max(p.doc_offsets[dc + 1] - beg, 0);
+    }
+  };
   auto issue_tile = [&](int stage, int tok_begin, int ntok) {
     // copy ntok (<= TOK) token rows starting at global token row tok_begin into stage
     const T* src = reinterpret_cast<const T*>(p.doc_tokens) + (size_t)tok_begin * d;
@@ -115,9 +125,7 @@ __global__ void __launch_bounds__(kMmaThreads) maxsim_mma_kernel(const MaxSimPar
   // cursor over (slot, tile) pairs
   int cur_slot = slot0, cur_tile = 0, cur_beg = 0, cur_len = 0;
   if (cur_slot < slot1) {
-    int dc = doc_of(cur_slot);
-    cur_beg = p.doc_offsets[dc];
-    cur_len = p.doc_offsets[dc + 1] - cur_beg;
+    doc_bounds(cur_slot, cur_beg, cur_len);
     issue_tile(0, cur_beg, min(TOK, cur_len));
   }
   cp_async_commit();
@@ -137,11 +145,7 @@ __global__ void __launch_bounds__(kMmaThreads) maxsim_mma_kernel(const MaxSimPar
     if (nxt_tile * TOK >= cur_len) {
       nxt_slot = cur_slot + 1;
       nxt_tile = 0;
-      if (nxt_slot < slot1) {
-        int dc = doc_of(nxt_slot);
-        nxt_beg = p.doc_offsets[dc];
-        nxt_len = p.doc_offsets[dc + 1] - nxt_beg;
-      }
+      if (nxt_slot < slot1) doc_bounds(nxt_slot, nxt_beg, nxt_len);
     }
     if (nxt_slot < slot1) issue_tile(stage ^ 1, nxt_beg + nxt_tile * TOK, min(TOK, nxt_len - nxt_tile * TOK));
     cp_async_commit();
@@ -335,7 +339,8 @@ __global__ void __launch_bounds__(kSimtThreads) maxsim_simt_kernel(const MaxSimP
   const int qi = blockIdx.y, slot = blockIdx.x;
   const int ndo = p.cand ? p.nc : p.nd;
   const int dc = p.cand ? p.cand[(size_t)qi * p.nc + slot] : slot;
-  const int beg = p.doc_offsets[dc], len = p.doc_offsets[dc + 1] - beg;
+  const bool in_range = dc >= 0 && dc < p.nd;  // outside the collection: an empty document, score -inf
+  const int beg = in_range ? p.doc_offsets[dc] : 0, len = in_range ? max(p.doc_offsets[dc + 1] - beg, 0) : 0;
   const float* qg = reinterpret_cast<const float*>(p.q) + (size_t)qi * lq * d;
   for (int i = tid; i < lq * d; i += kSimtThreads) Qs[i] = qg[i];
   for (int i = tid; i < 4 * lq; i += kSimtThreads) {

@@ -6,22 +6,31 @@
 // The stage is one contraction S = Q_all [nq*lq, d] . D_all^T [d, n_tokens] followed by a
 // segmented max over each document's tokens and a weighted sum over each query's tokens.
 // Mapping onto the hardware:
-//   * M (TMEM lanes) = query tokens, 128 per tile; N (TMEM columns) = document tokens, 256 per
-//     tile; K = d (64 or 128) fits one shared-memory stage, so there is no K pipeline.
-//     tcgen05.ld 32x32b hands thread t of an epilogue warp ONE query-token row with 32
-//     consecutive document tokens in registers, so the max over document tokens is a
-//     register-only FMNMX3 chain and the sum over a query's 32 tokens is one warp shuffle
-//     reduction.  The token-score matrix S exists only in TMEM.
-//   * each CTA keeps MG = 2 query tiles resident in shared memory (loaded once by TMA) and
-//     streams document-token tiles through a 2-stage TMA ring; every B tile feeds 2 MMAs.
-//     TMEM holds one 128x256 fp32 accumulator per resident query tile (2 x 256 = 512 columns);
-//     epilogue warp set s drains accumulator s while the tensor core fills the other one.
-//   * warp roles: 0 = TMA producer, 1 = MMA issuer (one elected thread), 2 = TMEM allocator,
-//     4..7 = epilogue set 0, 8..11 = epilogue set 1 (warp % 4 selects the TMEM lane quarter).
-//   * one CTA per SM; the (query-tile group, document) space is cut into equal contiguous spans, a
-//     span into segments at group boundaries (the query tiles are reloaded per segment).  A
-//     segment's tiles start at its first document's first token, so document boundaries are the only
-//     segmentation the epilogue has to track (prefetched two documents ahead).
+//   * M (TMEM lanes) = query tokens, N (TMEM columns) = document tokens, 256 per tile; K = d (64 or
+//     128) fits one shared-memory stage, so there is no K pipeline.  tcgen05.ld 32x32b hands thread t
+//     of an epilogue warp ONE query-token row with 32 consecutive document tokens in registers, so
+//     the max over document tokens is a register-only FMNMX3 chain and the sum over a query's 32
+//     tokens is one warp shuffle reduction.  The token-score matrix S exists only in TMEM.
+//   * CTA PAIRS (cta_group::2, a 2-wide cluster = the two SMs of a TPC): one tcgen05.mma of M = 256
+//     per K step; each CTA stages its own 128 query rows and HALF of the 256 document tokens of a
+//     tile (the tensor cores read the other half from the peer's shared memory), and holds its
+//     128 x 256 accumulator in its own TMEM.  A pair keeps MG = 2 "pair tiles" (2 x 256 query rows)
+//     resident, so every 64 KB document tile feeds 512 query rows and each SM pulls only 32 KB of
+//     it: half the L2->SM bytes and half the shared-memory operand reads per flop of the
+//     single-CTA version.  TMEM holds one accumulator per resident pair tile (2 x 256 columns);
+//     epilogue warp set s drains accumulator s while the tensor cores fill the other one.
+//   * warp roles (both CTAs): 0 = TMA producer (one lane per K half), 1 = MMA issuer (leader CTA
+//     only, one elected thread), 2 = TMEM allocator, 4..7 = epilogue set 0, 8..11 = epilogue set 1
+//     (warp % 4 selects the TMEM lane quarter).  TMA loads of both CTAs count on the LEADER's
+//     barriers; tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs; the
+//     epilogues hand accumulators back with a (remote) arrive on the leader's barrier.
+//   * work split: G query groups (512 query rows each) x R document ranges (equal token counts),
+//     pair p = (group p % G, range p / G).  The G pairs of one range walk the same documents at the
+//     same time, so a document tile comes from DRAM once and is served to the other groups out of
+//     L2 (the previous split let the groups drift a whole corpus apart: 6.2x DRAM re-reads).  With
+//     more groups than pairs, pair p runs groups p, p + P, ... over all documents.
+//   * query-token sums that span several warps (lq > 32) are combined through shared memory in a
+//     fixed order — results are run-to-run identical, like every other kernel of the library.
 #include <cuda.h>
 #include <math_constants.h>
 
@@ -33,18 +42,20 @@
 namespace rs {
 
 constexpr int kTcThreads = 384;
-constexpr int kTcBN = 256;      // document tokens per tile (UMMA N)
-constexpr int kTcMG = 2;        // resident query tiles per CTA == TMEM accumulator slots
-constexpr int kTcStages = 2;    // B ring depth
+constexpr int kTcBN = 256;      // document tokens per tile (UMMA N); each CTA of the pair stages half
+constexpr int kTcMG = 2;        // resident pair tiles (256 query rows each) == TMEM accumulators per CTA
+constexpr int kTcStages = 4;    // B ring depth (each stage: 128 tokens x d per CTA)
 constexpr int kTcTmemCols = 512;
+constexpr int kTcEpiBar = 2;    // named barriers 2, 3: the four warps of epilogue set 0 / 1
 
 struct MaxSimTcParams {
   const float* q_weight;
   const int32_t* doc_offsets;
   float* out;
   int32_t nq, lq, lq_pad, nd;
-  int32_t num_m_tiles, num_mgroups;
-  int32_t accumulate;  // lq_pad > 32: several warps contribute to one (query, doc) -> atomicAdd
+  int32_t num_pair_tiles;  // ceil(128-row query tiles / 2)
+  int32_t num_mgroups;     // G: groups of kTcMG pair tiles
+  int32_t ranges;          // R: document ranges per group (1 when G >= pairs)
 };
 
 __device__ __forceinline__ float tc_reference_weight(int i, int lq) {
@@ -62,42 +73,30 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     maxsim_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_d,
                       const MaxSimTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr uint32_t kABytesKH = 128 * 128;    // one K-half (64 elements) of a 128-row query tile
-  constexpr uint32_t kBBytesKH = kTcBN * 128;  // one K-half of a 256-token tile
+  constexpr uint32_t kABytesKH = 128 * 128;          // one K half (64 elements) of this CTA's 128 query rows
+  constexpr uint32_t kBBytesKH = (kTcBN / 2) * 128;  // one K half of this CTA's 128 document tokens
   constexpr uint32_t kABytes = kABytesKH * KH;
   constexpr uint32_t kBBytes = kBBytesKH * KH;
 
-  // ---- work of this CTA: a contiguous span of the (query group, document) space, cut into
-  // segments at query-group boundaries.  All SMs get the same number of documents (+-1) even when
-  // (groups x ranges) does not divide the SM count.
-  const int64_t units = (int64_t)p.num_mgroups * p.nd;
-  const int64_t u_begin = units * blockIdx.x / gridDim.x;
-  const int64_t u_end = units * (blockIdx.x + 1) / gridDim.x;
-  if (u_begin >= u_end) return;  // uniform: nothing allocated yet
-  struct Seg {
-    int mgroup, d0, d1;
-  };
-  auto seg_at = [&](int64_t u, Seg& sg) -> int64_t {  // segment starting at unit u; returns the next unit
-    sg.mgroup = (int)(u / p.nd);
-    sg.d0 = (int)(u - (int64_t)sg.mgroup * p.nd);
-    const int64_t left = u_end - u;
-    sg.d1 = (int)min((int64_t)p.nd, (int64_t)sg.d0 + left);
-    return u + (sg.d1 - sg.d0);
-  };
+  const uint32_t rank = cluster_ctarank();
+  const int pair = (int)(blockIdx.x >> 1), num_pairs = (int)(gridDim.x >> 1);
+  const int G = p.num_mgroups, R = p.ranges;
 
   // ---- shared memory carve-up (1024-byte aligned: SWIZZLE_128B atoms)
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
   uint8_t* smA = sm;                                 // [kTcMG][KH][128 rows x 128 B]
-  uint8_t* smB = smA + kTcMG * kABytes;              // [kTcStages][KH][256 rows x 128 B]
+  uint8_t* smB = smA + kTcMG * kABytes;              // [kTcStages][KH][128 rows x 128 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smB + kTcStages * kBBytes);
-  uint64_t* a_full = bars;                 // 1: query tiles of the current segment have landed
-  uint64_t* a_empty = bars + 1;            // 1: every MMA of the segment has read them
-  uint64_t* b_full = bars + 2;             // kTcStages
+  uint64_t* a_full = bars;                 // 1: query tiles of the current group have landed (leader's counts both CTAs)
+  uint64_t* a_empty = bars + 1;            // 1: every MMA of the group has read them
+  uint64_t* b_full = bars + 2;             // kTcStages (leader's)
   uint64_t* b_empty = b_full + kTcStages;  // kTcStages
   uint64_t* acc_full = b_empty + kTcStages;  // kTcMG
-  uint64_t* acc_empty = acc_full + kTcMG;    // kTcMG
+  uint64_t* acc_empty = acc_full + kTcMG;    // kTcMG (leader's collect both CTAs' epilogue warps)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + kTcMG);
+  int* s_range = reinterpret_cast<int*>(tmem_ptr + 2);   // [2] first / one-past-last document of this pair's range
+  float* parts = reinterpret_cast<float*>(s_range + 2);  // [2 sets][2 buffers][4 quarters] partial sums (lq > 32)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -110,64 +109,83 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
     for (int a = 0; a < kTcMG; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);  // the 4 warps of an epilogue set
+      mbar_init(&acc_empty[a], 2 * 4);  // the 4 warps of an epilogue set, in both CTAs
     }
     fence_mbar_init();
+    // This pair's document range: range r of R, cut where the running token count passes r/R of the total, so
+    // ragged documents give equal work.  Both CTAs compute the same bounds.
+    int d0 = 0, d1 = p.nd;
+    if (R > 1) {
+      const int r = pair / G;
+      const int64_t total = __ldg(p.doc_offsets + p.nd);
+      auto cut = [&](int rr) -> int {  // first document whose first token is at or after rr/R of all tokens
+        if (rr <= 0) return 0;
+        if (rr >= R) return p.nd;
+        const int64_t want = total * rr / R;
+        int lo = 0, hi = p.nd;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if ((int64_t)__ldg(p.doc_offsets + mid) < want) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+      };
+      d0 = cut(r);
+      d1 = cut(r + 1);
+    }
+    s_range[0] = d0;
+    s_range[1] = d1;
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr, kTcTmemCols);
-    tmem_relinquish();
+    tmem_alloc_cta2(tmem_ptr, kTcTmemCols);
+    tmem_relinquish_cta2();
   }
   tc5_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tc5_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr);
+  const int d0 = s_range[0], d1 = s_range[1];
 
   const int qpt = 128 / p.lq_pad;  // queries per 128-row tile
+  // groups of this pair: one (R > 1: group pair % G over its document range) or pair, pair + P, ... (all documents)
+  const int g_first = R > 1 ? pair % G : pair;
+  const int g_step = R > 1 ? G : num_pairs;
+  const int tok0 = d0 < d1 ? __ldg(p.doc_offsets + d0) : 0;
+  const int ntiles = d0 < d1 ? (__ldg(p.doc_offsets + d1) - tok0 + kTcBN - 1) / kTcBN : 0;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      tma_prefetch_desc(&map_q);
-      tma_prefetch_desc(&map_d);
+    // ------------------------------------------------------------------ TMA producer: lane kh loads K half kh
+    if (lane < KH && ntiles > 0) {
+      tma_prefetch_desc(lane == 0 ? &map_q : &map_d);
       const uint64_t pol = policy_evict_normal();
+      const uint32_t lead_a_full = mapa_u32(smem_u32(a_full), 0);
       int j = 0;  // B tiles issued so far (ring position)
       int seg_i = 0;
-      Seg sg;
-      for (int64_t u = u_begin; u < u_end; ++seg_i) {
-        u = seg_at(u, sg);
-        const int n_act = min(kTcMG, p.num_m_tiles - sg.mgroup * kTcMG);
-        const int tok0 = __ldg(p.doc_offsets + sg.d0);
-        const int ntiles = (__ldg(p.doc_offsets + sg.d1) - tok0 + kTcBN - 1) / kTcBN;
-        mbar_wait(a_empty, ((uint32_t)seg_i & 1u) ^ 1u);  // previous segment's MMAs are done with A
-        mbar_arrive_expect_tx(a_full, (uint32_t)n_act * kABytes);
+      for (int g = g_first; g < G; g += g_step, ++seg_i) {
+        const int n_act = min(kTcMG, p.num_pair_tiles - g * kTcMG);
+        mbar_wait(a_empty, ((uint32_t)seg_i & 1u) ^ 1u);  // previous group's MMAs are done with A (both CTAs)
+        if (rank == 0 && lane == 0) mbar_arrive_expect_tx(a_full, 2u * (uint32_t)n_act * kABytes);
         for (int a = 0; a < n_act; ++a)
-          for (int kh = 0; kh < KH; ++kh)
-            tma_load_3d(smA + a * kABytes + kh * kABytesKH, &map_q, kh * 64, 0, (sg.mgroup * kTcMG + a) * qpt, a_full,
-                        pol);
+          tma_load_3d_cta2(smA + a * kABytes + lane * kABytesKH, &map_q, lane * 64, 0,
+                           ((g * kTcMG + a) * 2 + (int)rank) * qpt, lead_a_full, pol);
         for (int t = 0; t < ntiles; ++t, ++j) {
           const int s = j % kTcStages;
           const uint32_t ph = (uint32_t)(j / kTcStages) & 1u;
           mbar_wait(&b_empty[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&b_full[s], kBBytes);
-          for (int kh = 0; kh < KH; ++kh)
-            tma_load_2d(smB + s * kBBytes + kh * kBBytesKH, &map_d, kh * 64, tok0 + t * kTcBN, &b_full[s], pol);
+          if (rank == 0 && lane == 0) mbar_arrive_expect_tx(&b_full[s], 2u * kBBytes);
+          tma_load_2d_cta2(smB + s * kBBytes + lane * kBBytesKH, &map_d, lane * 64,
+                           tok0 + t * kTcBN + (int)rank * (kTcBN / 2), mapa_u32(smem_u32(&b_full[s]), 0), pol);
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BF16, 128, kTcBN);
+    // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
+    if (lane == 0 && rank == 0 && ntiles > 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BF16, 256, kTcBN);
       int j = 0;
       int uses[kTcMG] = {0, 0};  // accumulator uses so far (phase of acc_empty / acc_full)
       int seg_i = 0;
-      Seg sg;
-      for (int64_t u = u_begin; u < u_end; ++seg_i) {
-        u = seg_at(u, sg);
-        const int n_act = min(kTcMG, p.num_m_tiles - sg.mgroup * kTcMG);
-        const int tok0 = __ldg(p.doc_offsets + sg.d0);
-        const int ntiles = (__ldg(p.doc_offsets + sg.d1) - tok0 + kTcBN - 1) / kTcBN;
+      for (int g = g_first; g < G; g += g_step, ++seg_i) {
+        const int n_act = min(kTcMG, p.num_pair_tiles - g * kTcMG);
         mbar_wait(a_full, (uint32_t)seg_i & 1u);
         for (int t = 0; t < ntiles; ++t, ++j) {
           const int s = j % kTcStages;
@@ -184,32 +202,30 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               const uint64_t db = umma_smem_desc_sw128(smem_u32(smB + s * kBBytes + kh * kBBytesKH));
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)  // 4 x UMMA_K(16 elements = 32 B) per 128-byte swizzle row
-                umma_f16_ss(tmem_base + (uint32_t)a * kTcBN, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
-                            (kh | kk) != 0 ? 1u : 0u);
+                umma_f16_ss_cta2(tmem_base + (uint32_t)a * kTcBN, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
+                                 (kh | kk) != 0 ? 1u : 0u);
             }
-            umma_commit(&acc_full[a]);  // accumulator a ready for its epilogue set
+            umma_commit_cta2(&acc_full[a], 0b11);  // accumulator a ready for its epilogue set in both CTAs
           }
-          umma_commit(&b_empty[s]);  // B stage reusable once both MMAs have read it
+          umma_commit_cta2(&b_empty[s], 0b11);  // B stage reusable (both CTAs) once the MMAs have read it
         }
-        umma_commit(a_empty);  // query tiles reusable once every MMA of the segment has completed
+        umma_commit_cta2(a_empty, 0b11);  // query tiles reusable once every MMA of the group has completed
       }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue sets
     const int set = (warp - 4) >> 2;
     const int quarter = warp & 3;  // TMEM lanes 32*quarter .. +31
-    int use = 0;                   // uses of this set's accumulator so far (phase of acc_full)
-    Seg sg;
-    for (int64_t u = u_begin; u < u_end;) {
-      u = seg_at(u, sg);
-      const int n_act = min(kTcMG, p.num_m_tiles - sg.mgroup * kTcMG);
-      if (set >= n_act) continue;  // this set's query tile does not exist in this group
-      const int d0 = sg.d0, d1 = sg.d1;
-      const int tok0 = __ldg(p.doc_offsets + d0);
-      const int ntiles = (__ldg(p.doc_offsets + d1) - tok0 + kTcBN - 1) / kTcBN;
-      const int mt = sg.mgroup * kTcMG + set;
-      const int row = quarter * 32 + lane;           // row in the 128-row tile
-      const int query = mt * qpt + row / p.lq_pad;   // uniform across the warp (lq_pad % 32 == 0)
+    const uint32_t lead_acc_empty = mapa_u32(smem_u32(&acc_empty[set]), 0);
+    const int qpw = p.lq_pad >> 5;  // warps (lane quarters) per query: 1, 2 or 4
+    int use = 0;                    // uses of this set's accumulator so far (phase of acc_full)
+    int fin = 0;                    // documents finalized so far (buffer of the cross-warp sum)
+    for (int g = g_first; g < G && ntiles > 0; g += g_step) {
+      const int n_act = min(kTcMG, p.num_pair_tiles - g * kTcMG);
+      if (set >= n_act) continue;  // this set's pair tile does not exist in this group
+      const int mt = ((g * kTcMG + set) << 1) + (int)rank;  // 128-row query tile of this CTA
+      const int row = quarter * 32 + lane;                  // row in the 128-row tile
+      const int query = mt * qpt + row / p.lq_pad;          // uniform across the warp (lq_pad % 32 == 0)
       const int tok = row % p.lq_pad;
       const bool q_valid = query < p.nq;
       float w = 0.f;
@@ -221,16 +237,25 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       int e1 = (d0 + 2 <= d1) ? __ldg(off + d0 + 2) - tok0 : INT_MAX;
       int e2 = (d0 + 3 <= d1) ? __ldg(off + d0 + 3) - tok0 : INT_MAX;
       float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
-      float* out_row = p.out + (size_t)query * p.nd;
+      float* out_row = p.out + (size_t)(q_valid ? query : 0) * p.nd;
 
       auto finalize = [&]() {
         const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         const float part = warp_sum(w != 0.f ? w * m : 0.f);
-        if (lane == 0 && q_valid) {
-          if (p.accumulate)
-            atomicAdd(out_row + doc, part);
-          else
-            out_row[doc] = part;
+        if (qpw == 1) {
+          if (lane == 0 && q_valid) out_row[doc] = part;
+        } else {
+          // the qpw warps of a query add their parts in a fixed order (all four warps of the set see the same
+          // document boundaries, so they meet here once per document)
+          float* pp = parts + ((set * 2 + (fin & 1)) << 2);
+          if (lane == 0) pp[quarter] = part;
+          named_bar_sync(kTcEpiBar + set, 128);
+          if (lane == 0 && (quarter & (qpw - 1)) == 0 && q_valid) {
+            float sum = pp[quarter];
+            for (int i = 1; i < qpw; ++i) sum += pp[quarter + i];
+            out_row[doc] = sum;
+          }
+          ++fin;
         }
         m0 = m1 = m2 = m3 = -CUDART_INF_F;
         ++doc;
@@ -248,7 +273,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       auto consume = [&](const uint32_t (&v)[32], int c0) {
         int a = 0;
         while (e0 <= c0 + 32) {  // warp-uniform
-          const int b = e0 - c0;  // 1..32: the current document ends before column b of this chunk
+          const int b = e0 - c0;  // 0..32: the current document ends before column b of this chunk
           float seg = -CUDART_INF_F;
 #pragma unroll
           for (int c = 0; c < 32; ++c) seg = fmaxf(seg, (c >= a && c < b) ? __uint_as_float(v[c]) : -CUDART_INF_F);
@@ -288,10 +313,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           if (ch + 2 < kTcBN / 32) {
             tmem_ld_32x32(taddr + (ch + 2) * 32, va);
           } else {
-            // all of this accumulator is in registers: hand the TMEM slot back to the MMA warp
+            // all of this accumulator is in registers: hand the TMEM slot back to the MMA warp of the leader
             tc5_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[set]);
+            if (lane == 0) mbar_arrive_cluster(lead_acc_empty);
           }
           consume(vb, cbase + (ch + 1) * 32);
           if (ch + 2 < kTcBN / 32) tmem_ld_wait(va);
@@ -301,10 +326,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   }
 
   tc5_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // the peer may still read this CTA's tiles / signal its barriers
   if (warp == 2) {
     tc5_fence_after();
-    tmem_dealloc(tmem_base, kTcTmemCols);
+    tmem_dealloc_cta2(tmem_base, kTcTmemCols);
   }
 }
 
@@ -386,7 +411,7 @@ bool tc5_has_encode(const Tc5State* s) { return s->encode != nullptr; }
 
 bool tc5_maxsim_supported(const Tc5State* s, int nq, int lq, int d, int nd, const int32_t* cand,
                           const int32_t* out_argmax) {
-  if (!s || !s->encode) return false;
+  if (!s || !s->encode || s->num_sms < 2) return false;
   if (cand != nullptr || out_argmax != nullptr) return false;
   if (d != 64 && d != 128) return false;
   if (lq < 1 || lq > 128 || nd < 1) return false;
@@ -398,10 +423,18 @@ int tc5_maxsim(Tc5State* s, const MaxSimParams& p, int dtype, cudaStream_t strea
   *launched = 0;
   const int lq_pad = p.lq <= 32 ? 32 : (p.lq <= 64 ? 64 : 128);
   const int qpt = 128 / lq_pad;
-  const int num_m_tiles = (p.nq + qpt - 1) / qpt;
-  const int mgroups = (num_m_tiles + kTcMG - 1) / kTcMG;
-  long long grid_ll = (long long)mgroups * p.nd;  // one CTA per SM, never more CTAs than work units
-  const int grid_x = (int)(grid_ll < s->num_sms ? grid_ll : s->num_sms);
+  const int num_m_tiles = (p.nq + qpt - 1) / qpt;          // 128-row query tiles
+  const int num_pair_tiles = (num_m_tiles + 1) / 2;         // 256-row tiles of a CTA pair
+  const int mgroups = (num_pair_tiles + kTcMG - 1) / kTcMG;  // G
+  // G groups x R document ranges of pairs; the G pairs of a range stream the same documents side by side.
+  const int pairs_avail = s->num_sms / 2;
+  int ranges = 1, pairs = pairs_avail;
+  if (mgroups < pairs_avail) {
+    ranges = pairs_avail / mgroups;
+    if (ranges > p.nd) ranges = p.nd;
+    if (ranges < 1) ranges = 1;
+    pairs = mgroups * ranges;
+  }
 
   CUtensorMap map_q, map_d;
   {
@@ -413,7 +446,7 @@ int tc5_maxsim(Tc5State* s, const MaxSimParams& p, int dtype, cudaStream_t strea
   {
     const uint64_t dims[2] = {(uint64_t)p.d, (uint64_t)p.n_tokens};
     const uint64_t strides[1] = {(uint64_t)p.d * 2};
-    const uint32_t box[2] = {64, (uint32_t)kTcBN};
+    const uint32_t box[2] = {64, (uint32_t)(kTcBN / 2)};  // each CTA of a pair stages half of a tile
     if (!tc5_encode(s, &map_d, dtype, 2, p.doc_tokens, dims, strides, box, err)) return -2;
   }
   MaxSimTcParams kp{};
@@ -424,27 +457,28 @@ int tc5_maxsim(Tc5State* s, const MaxSimParams& p, int dtype, cudaStream_t strea
   kp.lq = p.lq;
   kp.lq_pad = lq_pad;
   kp.nd = p.nd;
-  kp.num_m_tiles = num_m_tiles;
+  kp.num_pair_tiles = num_pair_tiles;
   kp.num_mgroups = mgroups;
-  kp.accumulate = lq_pad > 32 ? 1 : 0;
-  if (kp.accumulate) {
-    cudaError_t e = cudaMemsetAsync(p.out_scores, 0, (size_t)p.nq * p.nd * sizeof(float), stream);
-    if (e != cudaSuccess) {
-      *err = cudaGetErrorString(e);
-      return -3;
-    }
-  }
+  kp.ranges = ranges;
   const int kh = p.d / 64;
-  const size_t smem = 1024 + (size_t)kTcMG * 128 * 128 * kh + (size_t)kTcStages * kTcBN * 128 * kh + 256;
-  dim3 grid(grid_x);
+  const size_t smem = 1024 + (size_t)kTcMG * 128 * 128 * kh + (size_t)kTcStages * (kTcBN / 2) * 128 * kh + 512;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   cudaError_t e = cudaSuccess;
 #define RS_TC_LAUNCH(BF, KHV)                                                                                         \
   {                                                                                                                   \
     e = cudaFuncSetAttribute(maxsim_tc5_kernel<BF, KHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
-    if (e == cudaSuccess) {                                                                                           \
-      maxsim_tc5_kernel<BF, KHV><<<grid, kTcThreads, smem, stream>>>(map_q, map_d, kp);                              \
-      e = cudaGetLastError();                                                                                         \
-    }                                                                                                                 \
+    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, maxsim_tc5_kernel<BF, KHV>, map_q, map_d, kp);                 \
   }
   if (dtype == 1) {
     if (kh == 1) RS_TC_LAUNCH(true, 1) else RS_TC_LAUNCH(true, 2)

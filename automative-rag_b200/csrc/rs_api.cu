@@ -19,7 +19,12 @@ thread_local std::string g_create_error;
 struct rs_handle {
   int device = 0;
   int num_sms = 0;
-  cudaStream_t stream = nullptr;  // internal stream of the *_host entry points
+  // Stream ordering: every launch on this handle shares the workspaces below, so consecutive calls must not overlap
+  // on the device.  Calls on ONE stream are ordered by the stream; when the stream changes, the new stream waits for
+  // an event recorded on the previous one (order_after_last).
+  cudaStream_t last_stream = nullptr;
+  bool has_last = false;
+  cudaEvent_t order_ev = nullptr;
   // dense scan workspace
   uint64_t* ws_keys = nullptr;  // 2 x [num_sms, 2048]: consecutive scans alternate (they may overlap under PDL)
   unsigned* ticket = nullptr;   // 2 counters, 128 bytes apart
@@ -83,6 +88,20 @@ struct DeviceGuard {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Order the work about to be enqueued on `st` after everything this handle enqueued before.  Same stream: nothing to
+// do.  Different stream: event on the previous stream, wait on the new one.  (A previous stream the caller has
+// destroyed in the meantime has no pending work left to wait for; the failed record is ignored.)
+void order_after_last(rs_handle* h, cudaStream_t st) {
+  if (h->has_last && h->last_stream != st) {
+    if (cudaEventRecord(h->order_ev, h->last_stream) == cudaSuccess)
+      cudaStreamWaitEvent(st, h->order_ev, 0);
+    else
+      cudaGetLastError();
+  }
+  h->last_stream = st;
+  h->has_last = true;
+}
+
 int ensure_staging(rs_handle* h, size_t host_bytes, size_t dev_bytes) {
   if (host_bytes > h->pinned_bytes) {
     if (h->pinned) cudaFreeHost(h->pinned);
@@ -138,7 +157,7 @@ int rs_create(int device, rs_handle** out) {
   if (!h) return fail(nullptr, RS_ERR_NOMEM, "rs_create: out of host memory");
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
-  e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  e = cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc(&h->ws_keys, (size_t)2 * h->num_sms * kMaxK * sizeof(uint64_t));
   if (e == cudaSuccess) e = cudaMalloc(&h->ticket, 256);
   if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, 256);
@@ -165,7 +184,7 @@ int rs_destroy(rs_handle* h) {
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->dev_stage) cudaFree(h->dev_stage);
   if (h->filt_dev) cudaFree(h->filt_dev);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->order_ev) cudaEventDestroy(h->order_ev);
   delete h;
   return RS_OK;
 }
@@ -217,6 +236,7 @@ int rs_dense_topk(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_
   if (mask_stride_words < 0) return fail(h, RS_ERR_INVALID_ARG, "rs_dense_topk: negative mask stride");
   DeviceGuard guard(h->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  order_after_last(h, st);
 
   int impl = h->dense_impl;
   if (impl == RS_DENSE_AUTO) impl = rs::tc5_dense_supported(h->tc5, n, d, nq, k, mask, mask_stride_words) ? RS_DENSE_TCGEN05 : RS_DENSE_SCAN;
@@ -264,13 +284,16 @@ int rs_dense_topk(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_
 int rs_dense_topk_host(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_t dtype, const float* inv_norm,
                        int32_t metric, const void* queries_host, int32_t nq, const uint32_t* mask_host,
                        const uint32_t* mask_dev, int64_t mask_stride_words, int32_t k, int64_t id_base,
-                       float* out_scores_host, int64_t* out_ids_host) {
+                       float* out_scores_host, int64_t* out_ids_host, void* stream) {
   if (!h) return RS_ERR_INVALID_ARG;
   if (nq < 0 || n < 0) return fail(h, RS_ERR_INVALID_ARG, "rs_dense_topk_host: negative size");
   if (nq == 0) return RS_OK;
   if (!queries_host || !out_scores_host || !out_ids_host) return fail(h, RS_ERR_INVALID_ARG, "rs_dense_topk_host: NULL host buffer");
   if (d <= 0 || k < 1 || k > kMaxK) return fail(h, RS_ERR_INVALID_ARG, "rs_dense_topk_host: bad d/k");
   DeviceGuard guard(h->device);
+  // Everything runs on the CALLER's stream: the copy of the queries, the scan and the final synchronise are ordered
+  // after whatever the caller enqueued there before (rs_filter_mask building mask_dev, writes to the corpus).
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t q_bytes = align_up((size_t)nq * d * 2, 256);
   const size_t words_per_mask = (size_t)((n + 31) / 32);
   const size_t n_masks = mask_host ? (mask_stride_words ? (size_t)nq : 1) : 0;
@@ -284,7 +307,7 @@ int rs_dense_topk_host(rs_handle* h, const void* corpus, int64_t n, int32_t d, i
   uint8_t* dp = static_cast<uint8_t*>(h->dev_stage);
   memcpy(hp, queries_host, (size_t)nq * d * 2);
   if (mask_host) memcpy(hp + q_bytes, mask_host, ((n_masks - 1) * (size_t)mask_stride_words + words_per_mask) * 4);
-  cudaError_t e = cudaMemcpyAsync(dp, hp, q_bytes + m_bytes, cudaMemcpyHostToDevice, h->stream);
+  cudaError_t e = cudaMemcpyAsync(dp, hp, q_bytes + m_bytes, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return cuda_fail(h, e, "H2D(queries, mask)");
   const uint32_t* mask = mask_host ? reinterpret_cast<const uint32_t*>(dp + q_bytes) : mask_dev;
   // The k result pairs are written by the kernel straight into mapped pinned memory: no device-to-host copy to
@@ -293,9 +316,9 @@ int rs_dense_topk_host(rs_handle* h, const void* corpus, int64_t n, int32_t d, i
   float* d_scores = reinterpret_cast<float*>(hp_dev + q_bytes + m_bytes);
   int64_t* d_ids = reinterpret_cast<int64_t*>(hp_dev + q_bytes + m_bytes + os_bytes);
   rc = rs_dense_topk(h, corpus, n, d, dtype, inv_norm, metric, dp, nq, mask, mask_stride_words, k, id_base, d_scores,
-                     d_ids, h->stream);
+                     d_ids, stream);
   if (rc != RS_OK) return rc;
-  e = cudaStreamSynchronize(h->stream);
+  e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return cuda_fail(h, e, "rs_dense_topk_host: stream synchronize");
   memcpy(out_scores_host, hp + q_bytes + m_bytes, (size_t)nq * k * 4);
   memcpy(out_ids_host, hp + q_bytes + m_bytes + os_bytes, (size_t)nq * k * 8);
@@ -334,6 +357,7 @@ int rs_maxsim(rs_handle* h, const void* q, int32_t nq, int32_t lq, int32_t d, in
   if (dtype != RS_F16 && dtype != RS_BF16 && dtype != RS_F32) return fail(h, RS_ERR_UNSUPPORTED, "rs_maxsim: bad dtype %d", dtype);
   DeviceGuard guard(h->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  order_after_last(h, st);
   rs::MaxSimParams p{q, q_weight, doc_tokens, doc_offsets, cand, out_scores, out_argmax, n_tokens, nq, lq, d, nd, nc};
 
   if (dtype == RS_F32) {
@@ -417,6 +441,7 @@ int rs_filter_mask(rs_handle* h, const int32_t* const* cols, int32_t nclauses, c
   if (nclauses > 0 && (!cols || !values || !val_offsets)) return fail(h, RS_ERR_INVALID_ARG, "rs_filter_mask: NULL clause arrays");
   DeviceGuard guard(h->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  order_after_last(h, st);
   const int nvals = nclauses > 0 ? val_offsets[nclauses] : 0;
   const size_t ints = (size_t)nvals + nclauses + 1;
   if (ints > h->filt_dev_ints) {

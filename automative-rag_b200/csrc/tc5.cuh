@@ -112,6 +112,14 @@ __device__ __forceinline__ void tma_load_2d_cta2(void* dst, const CUtensorMap* m
       "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_cta2(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                                 uint32_t bar_cluster_addr, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_cta2(uint32_t* dst_smem, uint32_t ncols) {  // one warp in EACH CTA
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
                : "memory");

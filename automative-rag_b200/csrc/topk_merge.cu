@@ -8,11 +8,10 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "topk_merge.cuh"
 
 namespace rs {
 
-constexpr int kMergeThreads = 512;
-constexpr int kMergeBar = 1;
 
 // One CTA per query.  The candidates of the nlists sorted lists are loaded into shared memory as
 // (orderable score, position) keys and bitonic-sorted; runs of equal score are then ordered by
@@ -25,103 +24,16 @@ constexpr int kMergeBar = 1;
 // of those b_l, T — k_out or more candidates — so nothing below T is needed (everything equal to T
 // is kept).  148 lists x 100 (a batched dense search) shrink from a
 // 16384-key sort to a few hundred keys.
-__global__ void __launch_bounds__(kMergeThreads) topk_merge_kernel(const float* __restrict__ scores,
-                                                                   const int64_t* __restrict__ ids, int nlists, int nq,
-                                                                   int k_in, int k_out, int cap, int prune, int64_t sstride,
-                                                                   int64_t istride,
-                                                                   float* __restrict__ out_scores,
-                                                                   int64_t* __restrict__ out_ids) {
+//
+// The body lives in topk_merge.cuh (merge_one_query): the fused gather-and-merge kernel of the multi-GPU exchange
+// (comm.cu) runs the same code on lists that peers wrote into this GPU's wire buffer.
+__global__ void __launch_bounds__(kMergeThreads) topk_merge_kernel(const float* scores, const int64_t* ids, int nlists,
+                                                                   int nq, int k_in, int k_out, int cap, int prune,
+                                                                   int64_t sstride, int64_t istride, float* out_scores,
+                                                                   int64_t* out_ids) {
   extern __shared__ __align__(16) uint8_t smem[];
-  uint64_t* keys = reinterpret_cast<uint64_t*>(smem);  // [cap]
-  __shared__ int s_cnt;
-  __shared__ uint32_t s_t0;
-  const int q = blockIdx.x, tid = threadIdx.x;
-  const int m = nlists * k_in;
-  auto key_of = [&](int i) -> uint64_t {  // key of candidate i (list-major position), 0 when the slot is empty
-    const int list = i / k_in, j = i - list * k_in;
-    const size_t in_list = (size_t)q * k_in + j;
-    if (ids[(size_t)list * istride + in_list] < 0) return 0ull;
-    return make_key(scores[(size_t)list * sstride + in_list], (uint32_t)i);
-  };
-
-  uint32_t t0 = 0;  // orderable score below which a candidate cannot be in the answer (0 = keep everything)
-  if (prune) {
-    const int r = (k_out + nlists - 1) / nlists;  // <= k_in
-    const int need = (k_out + r - 1) / r;         // lists whose r-th entries bound the answer (<= nlists)
-    int n2 = 64;
-    while (n2 < nlists) n2 <<= 1;                 // <= cap
-    // per list: the smallest of its first r entries (its r-th best when the list is sorted; a valid bound for r of
-    // its entries in any case, so unsorted input lists are merely pruned less)
-    for (int l = tid; l < n2; l += kMergeThreads) {
-      uint64_t lo = 0ull;
-      if (l < nlists) {
-        lo = ~0ull;
-        for (int j = 0; j < r; ++j) {
-          const uint64_t kj = key_of(l * k_in + j);
-          lo = kj < lo ? kj : lo;
-        }
-        lo = (lo & 0xFFFFFFFF00000000ull) | 1ull;  // score field only; an empty slot among the r gives score 0
-      }
-      keys[l] = lo;
-    }
-    bitonic_sort_desc(keys, n2, tid, kMergeThreads, kMergeBar);
-    if (tid == 0) {
-      s_t0 = (uint32_t)(keys[need - 1] >> 32);  // 0 if fewer than `need` lists have r entries: no pruning
-      s_cnt = 0;
-    }
-    named_bar_sync(kMergeBar, kMergeThreads);
-    t0 = s_t0;
-    named_bar_sync(kMergeBar, kMergeThreads);  // everyone has read keys[] / s_t0 before keys[] is refilled
-  }
-  int n_sort = cap;
-  if (t0 != 0) {
-    for (int i = tid; i < m; i += kMergeThreads) {
-      const uint64_t key = key_of(i);
-      if (key != 0ull && (uint32_t)(key >> 32) >= t0) keys[atomicAdd(&s_cnt, 1)] = key;
-    }
-    named_bar_sync(kMergeBar, kMergeThreads);
-    const int kept = s_cnt;
-    n_sort = 64;
-    while (n_sort < kept) n_sort <<= 1;
-    for (int i = kept + tid; i < n_sort; i += kMergeThreads) keys[i] = 0ull;
-  } else {
-    for (int i = tid; i < cap; i += kMergeThreads) keys[i] = i < m ? key_of(i) : 0ull;
-  }
-  bitonic_sort_desc(keys, n_sort, tid, kMergeThreads, kMergeBar);
-  // position in the final order: rank inside the run of equal scores is by ascending id
-  for (int i = tid; i < min(m, n_sort); i += kMergeThreads) {
-    const uint64_t key = keys[i];
-    if (key == 0ull) continue;
-    const uint32_t so = (uint32_t)(key >> 32);
-    const int pos = (int)key_row(key);
-    const int64_t id = ids[(size_t)(pos / k_in) * istride + (size_t)q * k_in + (pos % k_in)];
-    int lo = i;
-    while (lo > 0 && (uint32_t)(keys[lo - 1] >> 32) == so) --lo;
-    int rank = 0;
-    bool tie = (lo != i) || (i + 1 < n_sort && (uint32_t)(keys[i + 1] >> 32) == so && keys[i + 1] != 0ull);
-    if (tie) {
-      for (int j = lo; j < n_sort && keys[j] != 0ull && (uint32_t)(keys[j] >> 32) == so; ++j) {
-        const int pj = (int)key_row(keys[j]);
-        const int64_t idj = ids[(size_t)(pj / k_in) * istride + (size_t)q * k_in + (pj % k_in)];
-        if (idj < id || (idj == id && j < i)) ++rank;
-      }
-    } else {
-      lo = i;
-    }
-    const int dst = lo + rank;
-    if (dst < k_out) {
-      out_scores[(size_t)q * k_out + dst] = key_score(key);
-      out_ids[(size_t)q * k_out + dst] = id;
-    }
-  }
-  // padding
-  named_bar_sync(kMergeBar, kMergeThreads);
-  for (int i = tid; i < k_out; i += kMergeThreads) {
-    if (i >= n_sort || keys[i] == 0ull) {
-      out_scores[(size_t)q * k_out + i] = -CUDART_INF_F;
-      out_ids[(size_t)q * k_out + i] = -1;
-    }
-  }
+  merge_one_query(reinterpret_cast<uint64_t*>(smem), scores, ids, nlists, k_in, k_out, cap, prune, sstride, istride,
+                  out_scores, out_ids, (int)blockIdx.x);
 }
 
 cudaError_t launch_topk_merge(const float* scores, const int64_t* ids, int nlists, int nq, int k_in, int k_out,
@@ -129,14 +41,11 @@ cudaError_t launch_topk_merge(const float* scores, const int64_t* ids, int nlist
                               cudaStream_t stream) {
   if (score_list_stride == 0) score_list_stride = (int64_t)nq * k_in;
   if (id_list_stride == 0) id_list_stride = (int64_t)nq * k_in;
-  int cap = 64;
-  while (cap < nlists * k_in) cap <<= 1;
+  int cap, prune;
+  merge_plan(nlists, k_in, k_out, &cap, &prune);
   const size_t smem = (size_t)cap * 8;
   cudaError_t e = cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  // pruning pays once the full sort is large and needs the lists' r-th entries (r <= k_in) and a small sort of them
-  const int r = (k_out + nlists - 1) / nlists;
-  const int prune = (cap >= 2048 && nlists >= 2 && nlists <= 2048 && r <= k_in) ? 1 : 0;
   topk_merge_kernel<<<nq, kMergeThreads, smem, stream>>>(scores, ids, nlists, nq, k_in, k_out, cap, prune,
                                                          score_list_stride, id_list_stride, out_scores, out_ids);
   return cudaGetLastError();

@@ -53,7 +53,7 @@ int main(void) {
     for (i = 0; i < N; ++i) corpus[(size_t)i * D + i % D] = f32_to_f16((float)(i / D + 1)); /* row i = (i/D + 1) e_(i%D) */
     for (i = 0; i < D; ++i) query[i] = f32_to_f16(i == 7 ? 1.0f : 0.0f);                     /* q = e_7 */
     if (cudaMalloc(&dcorpus, (size_t)N * D * 2) != 0 || cudaMemcpy(dcorpus, corpus, (size_t)N * D * 2, 1) != 0) return 1;
-    rc = rs_dense_topk_host(h, dcorpus, N, D, RS_F16, NULL, RS_METRIC_IP, query, 1, NULL, NULL, 0, K, 0, scores, ids);
+    rc = rs_dense_topk_host(h, dcorpus, N, D, RS_F16, NULL, RS_METRIC_IP, query, 1, NULL, NULL, 0, K, 0, scores, ids, NULL);
     if (rc != RS_OK) {
       printf("rs_dense_topk_host: %s\n", rs_last_error(h));
       return 1;

@@ -42,6 +42,10 @@
  * Threading: one handle per (process, device); calls on one handle must be
  * serialised by the caller.  Kernels are stream-ordered on the `stream`
  * argument (a cudaStream_t passed as void*; NULL = legacy default stream).
+ * All launches of a handle share its workspaces: when consecutive calls name
+ * DIFFERENT streams the engine orders the later call after the earlier one with
+ * an event, so calls never overlap on the device whatever streams they use.  A
+ * stream passed to the handle must stay alive until the next call on the handle.
  */
 #ifndef RAG_B200_H_
 #define RAG_B200_H_
@@ -52,7 +56,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 1
+#define RS_ABI_VERSION 2
 
 typedef struct rs_handle rs_handle;
 
@@ -135,15 +139,17 @@ int rs_dense_topk(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_
                   float* out_scores, int64_t* out_ids, void* stream);
 
 /* Same search with HOST query / mask / output buffers (the call the Python adapter makes
- * per request): copies queries (+mask when given) host->device, runs rs_dense_topk on the
- * handle's stream, copies the k results device->host and synchronises.  The corpus and
- * inv_norm stay resident on the device.  mask_host may be NULL; mask_dev is used when
- * mask_host is NULL (either may be NULL = no filter). */
+ * per request): copies queries (+mask when given) host->device, runs rs_dense_topk, brings the
+ * k results back and synchronises — all on `stream`, the CALLER's stream, so the search is
+ * ordered after whatever the caller enqueued there before (rs_filter_mask writing mask_dev,
+ * appends to the corpus, tombstone updates).  The corpus and inv_norm stay resident on the
+ * device.  mask_host may be NULL; mask_dev is used when mask_host is NULL (either may be
+ * NULL = no filter). */
 int rs_dense_topk_host(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_t dtype,
                        const float* inv_norm, int32_t metric, const void* queries_host,
                        int32_t nq, const uint32_t* mask_host, const uint32_t* mask_dev,
                        int64_t mask_stride_words, int32_t k, int64_t id_base,
-                       float* out_scores_host, int64_t* out_ids_host);
+                       float* out_scores_host, int64_t* out_ids_host, void* stream);
 
 /*
  * Merge `nlists` per-shard top-k lists into one.  Inputs laid out as the all-gather

@@ -68,9 +68,9 @@ def test_scan_shared_memory_plan_invariants():
 
 def test_library_loads_and_reports_abi_version():
     lib = rag.load_library()
-    assert lib.rs_abi_version() == 1
+    assert lib.rs_abi_version() == 2
     m = re.search(r"#define RS_ABI_VERSION (\d+)", open(os.path.join(ROOT, "include", "rag_b200.h")).read())
-    assert int(m.group(1)) == 1
+    assert int(m.group(1)) == 2
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -115,7 +115,7 @@ def test_header_is_plain_c_and_the_c_client_links(tmp_path):
     if torch.cuda.is_available():
         return  # the device part is exercised on the GPU box (profiles/r01_c_client.txt)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
-    assert r.returncode == 0 and "ABI version 1" in r.stdout and "no CPU fallback" in r.stdout
+    assert r.returncode == 0 and "ABI version 2" in r.stdout and "no CPU fallback" in r.stdout
 
 
 def test_sass_of_the_hot_kernels_uses_the_blackwell_units():

@@ -169,3 +169,72 @@ def test_hybrid_retriever_composition(store):
     assert seconds > 0
     assert len(out) == 5 and all(d.metadata["manufacturer"] == "Honda" for d, _ in out)
     assert [s for _, s in out] == sorted([s for _, s in out], reverse=True)
+
+
+# ------------------------------------------------------------------------------------------ stream ordering
+def _big_collection(n, dim=256, seed=11):
+    """A collection filled through Collection.upsert with device-generated vectors (the embedding model is out of
+    scope) and a payload whose fields cycle with the row index, so filters have a closed-form answer."""
+    client = rag.B200Client(0)
+    col = client.create_collection(f"big-{np.random.randint(1 << 30)}", size=dim)
+    g = torch.Generator(device=col.device).manual_seed(seed)
+    vec = torch.randn(n, dim, generator=g, device=col.device)
+    makers = ["Toyota", "Honda", "BMW", "Ford", "Kia"]
+    payloads = [{"page_content": f"c{i}", "metadata": {"manufacturer": makers[i % 5], "year": 2000 + i % 7,
+                                                         "category": ["sedan", "suv", "truck"][i % 3]}}
+                for i in range(n)]
+    return client, col, vec, payloads
+
+
+def test_search_is_ordered_after_upsert_and_mask_build_on_the_callers_stream():
+    """the host entry point used a private non-blocking stream, so a search could start before
+    the upsert / rs_filter_mask enqueued just before it on torch's stream had finished.  400k rows are appended and
+    IMMEDIATELY searched with a 16-clause filter (a long mask kernel), with no synchronise in between; repeated so a
+    race would show.  The expected answer is computed with torch on the same device after a full synchronise."""
+    from automative_rag_b200.filters import FieldCondition, Filter, MatchValue, Range
+
+    n, dim, k = 400_000, 256, 16
+    client, col, vec, payloads = _big_collection(n, dim)
+    conds = [FieldCondition(key="metadata.manufacturer", match=MatchValue(value="Honda")),
+             FieldCondition(key="metadata.year", range=Range(gte=2003, lte=2003))]
+    flt = Filter(must=(conds * 8))  # 16 clauses: the mask kernel reads 16 columns x 400k rows
+    q = torch.randn(dim, generator=torch.Generator().manual_seed(5))
+    for rep in range(3):
+        ids = [f"p{rep}-{i}" for i in range(n)]
+        if rep:
+            col.delete([f"p{rep - 1}-{i}" for i in range(n)])
+        col.upsert(ids, vec + rep, payloads)                      # device writes on torch's current stream
+        mask = col.device_mask(flt)                                # rs_filter_mask on torch's current stream
+        scores, rows = col.engine.dense_topk_host(
+            col.vectors[: col.n], q.to(col.dtype).contiguous(), k, mask_dev=mask, inv_norm=col.inv_norm[: col.n],
+            metric=rag._ffi.RS_METRIC_COSINE)
+        torch.cuda.synchronize()
+        base = rep * n
+        i = torch.arange(n, device=col.device)
+        passing = ((i % 5) == 1) & ((i % 7) == 3)
+        stored = col.vectors[base: base + n].float()
+        ref = (stored @ q.to(col.device).half().float()) * col.inv_norm[base: base + n] / q.half().float().norm().to(col.device)
+        ref = torch.where(passing, ref, torch.full_like(ref, float("-inf")))
+        ws, wi = torch.topk(ref, k)
+        assert rows[0].tolist() == (wi + base).cpu().tolist(), f"rep {rep}: stale mask / corpus read by the scan"
+        np.testing.assert_allclose(scores[0].numpy(), ws.cpu().numpy(), rtol=1e-3, atol=1e-6)
+
+
+def test_calls_on_different_streams_do_not_overlap_on_the_shared_workspace(engine):
+    """scans on two streams share one workspace; the handle orders a call after the previous one
+    when the stream changes.  Alternating streams with no host synchronise must give the single-stream answers."""
+    dev = engine.device
+    g = torch.Generator(device=dev).manual_seed(3)
+    c = torch.randn(300_000, 256, generator=g, device=dev)
+    c = (c / c.norm(dim=1, keepdim=True)).half()
+    qs = torch.randn(12, 256, generator=g, device=dev).half()
+    want = [engine.dense_topk(c, qs[j], 50) for j in range(12)]
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    got = []
+    for j in range(12):
+        with torch.cuda.stream(s1 if j % 2 == 0 else s2):
+            got.append(engine.dense_topk(c, qs[j], 50))
+    torch.cuda.synchronize()
+    for (ws, wi), (gs, gi) in zip(want, got):
+        assert torch.equal(wi, gi) and torch.equal(ws, gs)
