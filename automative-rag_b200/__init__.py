@@ -11,7 +11,8 @@ does, and raises when the library or a B200 is missing — there is no CPU fallb
 """
 from . import _ffi
 from ._ffi import Engine, EngineError, get_engine, load_library
-from .distributed import ShardedCandidateMaxSim, ShardedDenseIndex, ShardedMaxSim, partition_candidates, shard_bounds
+from .distributed import (ShardedCandidateMaxSim, ShardedDenseIndex, ShardedMaxSim, owned_candidates,
+                          partition_candidates, shard_bounds)
 from .documents import Document
 from .filters import FieldCondition, Filter, MatchValue, Range, build_filter
 from .rerankers import B200ColBERTReranker, pack_documents
@@ -22,5 +23,6 @@ __all__ = [
     "Engine", "EngineError", "get_engine", "load_library", "Document", "Filter", "FieldCondition", "MatchValue",
     "Range", "build_filter", "B200Client", "B200VectorStore", "Collection", "B200ColBERTReranker", "pack_documents",
     "HybridRetriever", "ShardedDenseIndex", "ShardedMaxSim", "ShardedCandidateMaxSim", "partition_candidates",
+    "owned_candidates",
     "shard_bounds",
 ]

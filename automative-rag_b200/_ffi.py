@@ -16,7 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "librag_b200.so")
 
 ABI_VERSION = 2
-RS_OK, RS_ERR_INVALID_ARG, RS_ERR_UNSUPPORTED, RS_ERR_CUDA, RS_ERR_NO_DEVICE, RS_ERR_NOMEM = 0, -1, -2, -3, -4, -5
+RS_OK, RS_ERR_INVALID_ARG, RS_ERR_UNSUPPORTED, RS_ERR_CUDA, RS_ERR_NO_DEVICE, RS_ERR_NOMEM, RS_ERR_COMM = 0, -1, -2, -3, -4, -5, -6
+RS_COMM_HANDLE_BYTES, RS_COMM_MAX_WORLD = 128, 8
 RS_F16, RS_BF16, RS_F32 = 0, 1, 2
 RS_METRIC_IP, RS_METRIC_COSINE = 0, 1
 RS_MAXSIM_AUTO, RS_MAXSIM_MMA, RS_MAXSIM_TCGEN05, RS_MAXSIM_SIMT, RS_MAXSIM_TCGEN05_CAND = 0, 1, 2, 3, 4
@@ -39,9 +40,17 @@ SIGNATURES = {
     "rs_dense_topk": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _I32, _P, _I64, _I32, _I64, _P, _P, _P]),
     "rs_dense_topk_host": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _I32, _P, _P, _I64, _I32, _I64, _P, _P, _P]),
     "rs_topk_merge": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I64, _I64, _P, _P, _P]),
-    "rs_maxsim": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _I64, _P, _I32, _P, _I32, _P, _P, _P]),
+    "rs_maxsim": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _I64, _P, _I32, _P, _I32, _P, _P, _P, _P]),
     "rs_rerank_postprocess": (C.c_int, [_P, _P, _P, _I32, _I32, _F, _F, _I32, _P, _P, _P]),
     "rs_filter_mask": (C.c_int, [_P, C.POINTER(_P), _I32, C.POINTER(_I32), C.POINTER(_I32), _P, _I64, _P, _P]),
+    "rs_comm_export": (C.c_int, [_P, _I32, _I32, _I64, _P]),
+    "rs_comm_open": (C.c_int, [_P, _P]),
+    "rs_comm_close": (C.c_int, [_P]),
+    "rs_comm_info": (C.c_int, [_P, C.POINTER(_I32), C.POINTER(_I32), C.POINTER(_I64)]),
+    "rs_allgather_topk": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P]),
+    "rs_allgather": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "rs_allreduce_max_f32": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "rs_dense_topk_sharded_host": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _I32, _P, _I64, _I32, _I64, _P, _P, _P]),
 }
 
 _lib = None
@@ -123,7 +132,7 @@ class Engine:
         if rc == RS_OK:
             return
         msg = self._lib.rs_last_error(self._h).decode()
-        if rc in (RS_ERR_INVALID_ARG, RS_ERR_UNSUPPORTED):
+        if rc in (RS_ERR_INVALID_ARG, RS_ERR_UNSUPPORTED):  # RS_ERR_COMM and CUDA errors raise EngineError
             raise ValueError(f"{what}: {msg}")
         raise EngineError(f"{what} failed ({rc}): {msg}")
 
@@ -252,9 +261,10 @@ class Engine:
     # -- MaxSim -------------------------------------------------------------------------------
     def maxsim(self, q: torch.Tensor, doc_tokens: torch.Tensor, doc_offsets: torch.Tensor, *,
                q_weight: Optional[torch.Tensor] = None, cand: Optional[torch.Tensor] = None,
-               want_argmax: bool = False):
+               want_argmax: bool = False, want_tokmax: bool = False):
         """q [nq, lq, d]; doc_tokens [T, d]; doc_offsets int32 [nd+1]; cand None or int32 [nq, nc].
-        Returns scores [nq, nd|nc] fp32 (and argmax int32 [nq, nd|nc, lq] when requested)."""
+        Returns scores [nq, nd|nc] fp32; with want_argmax also argmax int32 [nq, nd|nc, lq]; with want_tokmax also
+        the per-query-token maxima fp32 [nq, nd|nc, lq] (in that order)."""
         self._dev(q, "q")
         self._dev(doc_tokens, "doc_tokens")
         self._dev(doc_offsets, "doc_offsets")
@@ -279,11 +289,13 @@ class Engine:
         ndo = nc if cand is not None else nd
         out = torch.empty(nq, ndo, dtype=torch.float32, device=self.device)
         arg = torch.empty(nq, ndo, lq, dtype=torch.int32, device=self.device) if want_argmax else None
+        tmax = torch.empty(nq, ndo, lq, dtype=torch.float32, device=self.device) if want_tokmax else None
         rc = self._lib.rs_maxsim(self._h, _ptr(q), nq, lq, d, dtype_code(q.dtype), _ptr(q_weight), _ptr(doc_tokens),
                                  doc_tokens.shape[0], _ptr(doc_offsets), nd, _ptr(cand), nc, _ptr(out), _ptr(arg),
-                                 _stream_ptr(self.device))
+                                 _ptr(tmax), _stream_ptr(self.device))
         self._check(rc, "rs_maxsim")
-        return (out, arg) if want_argmax else out
+        res = (out,) + ((arg,) if want_argmax else ()) + ((tmax,) if want_tokmax else ())
+        return res if len(res) > 1 else out
 
     def rerank_postprocess(self, scores: torch.Tensor, other: Optional[torch.Tensor], top_k: int,
                            w_a: float = 0.8, w_b: float = 0.2):
@@ -303,6 +315,94 @@ class Engine:
                                              _ptr(out), _stream_ptr(self.device))
         self._check(rc, "rs_rerank_postprocess")
         return idx, out
+
+    # -- multi-GPU exchange over peer memory -----------------------------------------------------
+    def comm_init(self, group=None, slot_bytes: int = 4 << 20) -> None:
+        """Open the peer-memory exchange with the ranks of `group` (one process per GPU): export this rank's wire
+        block, exchange the 128-byte handles through torch.distributed, map the peers.  `slot_bytes` bounds one
+        rank's contribution per collective (nq * k * 12 bytes for top-k lists, 4 bytes per score)."""
+        import torch.distributed as dist
+
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        blob = C.create_string_buffer(RS_COMM_HANDLE_BYTES)
+        self._check(self._lib.rs_comm_export(self._h, world, rank, slot_bytes, blob), "rs_comm_export")
+        blobs: list = [None] * world
+        dist.all_gather_object(blobs, bytes(blob.raw), group=group)
+        allb = C.create_string_buffer(b"".join(blobs), RS_COMM_HANDLE_BYTES * world)
+        self._check(self._lib.rs_comm_open(self._h, allb), "rs_comm_open")
+        dist.barrier(group)  # every rank has mapped every block before the first collective
+
+    def comm_close(self) -> None:
+        self._check(self._lib.rs_comm_close(self._h), "rs_comm_close")
+
+    @property
+    def comm_world(self) -> int:
+        w = _I32(0)
+        self._lib.rs_comm_info(self._h, C.byref(w), None, None)
+        return int(w.value)
+
+    def allgather_topk(self, local_scores: torch.Tensor, local_ids: torch.Tensor, k_out: int,
+                       out_scores: Optional[torch.Tensor] = None, out_ids: Optional[torch.Tensor] = None):
+        """local [nq, k_in] (this rank's top-k, global ids) -> merged global ([nq, k_out], [nq, k_out]) on every rank."""
+        self._dev(local_scores, "local_scores")
+        self._dev(local_ids, "local_ids")
+        if local_scores.dtype != torch.float32 or local_ids.dtype != torch.int64 or local_scores.shape != local_ids.shape \
+                or local_scores.dim() != 2:
+            raise ValueError("local_scores float32 / local_ids int64 of identical shape [nq, k_in] expected")
+        nq, k_in = local_scores.shape
+        if out_scores is None:
+            out_scores = torch.empty(nq, k_out, dtype=torch.float32, device=self.device)
+        if out_ids is None:
+            out_ids = torch.empty(nq, k_out, dtype=torch.int64, device=self.device)
+        rc = self._lib.rs_allgather_topk(self._h, _ptr(local_scores), _ptr(local_ids), nq, k_in, k_out, _ptr(out_scores),
+                                         _ptr(out_ids), _stream_ptr(self.device))
+        self._check(rc, "rs_allgather_topk")
+        return out_scores, out_ids
+
+    def allgather(self, local: torch.Tensor) -> torch.Tensor:
+        """[...] on every rank -> [world, ...] (same shape and dtype on every rank; bytes a multiple of 16)."""
+        self._dev(local, "local")
+        out = torch.empty((self.comm_world,) + tuple(local.shape), dtype=local.dtype, device=self.device)
+        rc = self._lib.rs_allgather(self._h, _ptr(local), local.numel() * local.element_size(), _ptr(out),
+                                    _stream_ptr(self.device))
+        self._check(rc, "rs_allgather")
+        return out
+
+    def allreduce_max(self, local: torch.Tensor) -> torch.Tensor:
+        """Element-wise max over ranks of a float32 tensor."""
+        self._dev(local, "local")
+        if local.dtype != torch.float32:
+            raise ValueError("allreduce_max takes float32")
+        out = torch.empty_like(local)
+        rc = self._lib.rs_allreduce_max_f32(self._h, _ptr(local), local.numel(), _ptr(out), _stream_ptr(self.device))
+        self._check(rc, "rs_allreduce_max_f32")
+        return out
+
+    def dense_topk_sharded_host(self, corpus: torch.Tensor, queries_host: torch.Tensor, k: int, *,
+                                mask_dev: Optional[torch.Tensor] = None, inv_norm: Optional[torch.Tensor] = None,
+                                metric: int = RS_METRIC_COSINE, id_base: int = 0,
+                                out_scores: Optional[torch.Tensor] = None, out_ids: Optional[torch.Tensor] = None):
+        """Per-request call against this rank's row shard: HOST queries in, merged global HOST (scores, ids) out."""
+        self._dev(corpus, "corpus")
+        if queries_host.dim() == 1:
+            queries_host = queries_host.unsqueeze(0)
+        if queries_host.device.type != "cpu" or not queries_host.is_contiguous() or queries_host.dtype != corpus.dtype:
+            raise ValueError("queries_host must be a contiguous CPU tensor of the corpus dtype")
+        n, d = corpus.shape
+        nq = queries_host.shape[0]
+        stride = 0
+        if mask_dev is not None:
+            self._dev(mask_dev, "mask_dev")
+            stride = (n + 31) // 32 if mask_dev.dim() == 2 else 0
+        if out_scores is None:
+            out_scores = torch.empty(nq, k, dtype=torch.float32)
+        if out_ids is None:
+            out_ids = torch.empty(nq, k, dtype=torch.int64)
+        rc = self._lib.rs_dense_topk_sharded_host(self._h, _ptr(corpus), n, d, dtype_code(corpus.dtype), _ptr(inv_norm),
+                                                  metric, _ptr(queries_host), nq, _ptr(mask_dev), stride, k, id_base,
+                                                  _ptr(out_scores), _ptr(out_ids), _stream_ptr(self.device))
+        self._check(rc, "rs_dense_topk_sharded_host")
+        return out_scores, out_ids
 
     def filter_mask(self, columns: Sequence[torch.Tensor], value_sets: Sequence[Sequence[int]], n: int,
                     tombstone: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "librag_b200.so")
-SOURCES = ["rs_api.cu", "dense_scan.cu", "topk_merge.cu", "maxsim_mma.cu", "maxsim_tc5.cu", "maxsim_cand_tc5.cu", "dense_tc5.cu"]
+SOURCES = ["rs_api.cu", "dense_scan.cu", "topk_merge.cu", "maxsim_mma.cu", "maxsim_tc5.cu", "maxsim_cand_tc5.cu", "dense_tc5.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

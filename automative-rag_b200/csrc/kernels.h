@@ -56,6 +56,7 @@ struct MaxSimParams {
   const int32_t* cand;         // null or [nq, nc]
   float* out_scores;           // [nq, ndo]   ndo = cand ? nc : nd
   int32_t* out_argmax;         // null or [nq, ndo, lq]
+  float* out_tokmax;           // null or [nq, ndo, lq]: the per-query-token maxima themselves
   int64_t n_tokens;            // rows in doc_tokens
   int32_t nq, lq, d, nd, nc;
 };

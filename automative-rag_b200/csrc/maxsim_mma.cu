@@ -247,7 +247,8 @@ __global__ void __launch_bounds__(kMmaThreads) maxsim_mma_kernel(const MaxSimPar
           if (i < p.lq) {
             float w = wts[i];
             if (w != 0.f) part = fmaf(w, v, part);
-            if (ARGMAX) p.out_argmax[((size_t)qi * ndo + cur_slot) * p.lq + i] = ix;
+            if (ARGMAX && p.out_argmax) p.out_argmax[((size_t)qi * ndo + cur_slot) * p.lq + i] = ix;
+            if (ARGMAX && p.out_tokmax) p.out_tokmax[((size_t)qi * ndo + cur_slot) * p.lq + i] = v;
           }
         }
         part = warp_sum(part);
@@ -285,7 +286,7 @@ size_t maxsim_mma_smem_bytes(int lq, int d) {
 
 template <typename T, int MT, int NT>
 static cudaError_t launch_mma_cfg(const MaxSimParams& p, int num_sms, cudaStream_t stream) {
-  const bool argmax = p.out_argmax != nullptr;
+  const bool argmax = p.out_argmax != nullptr || p.out_tokmax != nullptr;
   const int ndo = p.cand ? p.nc : p.nd;
   const size_t smem = maxsim_mma_smem_bytes_impl(MT, NT, p.d, argmax);
   long long pairs = (long long)p.nq * ndo;
@@ -378,6 +379,7 @@ __global__ void __launch_bounds__(kSimtThreads) maxsim_simt_kernel(const MaxSimP
       float w = p.q_weight ? p.q_weight[(size_t)qi * lq + i] : reference_weight(i, lq);
       if (w != 0.f) part = fmaf(w, v, part);
       if (p.out_argmax) p.out_argmax[((size_t)qi * ndo + slot) * lq + i] = ix;
+      if (p.out_tokmax) p.out_tokmax[((size_t)qi * ndo + slot) * lq + i] = v;
     }
     // fixed-order sum over lanes so the result is run-to-run deterministic
     part = warp_sum(part);

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/rag_b200.h"
+#include "comm.h"
 #include "kernels.h"
 #include "tc5_host.h"
 
@@ -43,6 +44,11 @@ struct rs_handle {
   size_t filt_dev_ints = 0;
   // tcgen05 paths (tensor-map cache, scratch)
   rs::Tc5State* tc5 = nullptr;
+  // multi-GPU exchange over peer memory (comm.cu)
+  rs::CommState* comm = nullptr;
+  float* shard_scores = nullptr;  // local top-k of rs_dense_topk_sharded_host before the exchange
+  int64_t* shard_ids = nullptr;
+  size_t shard_pairs = 0;
   int dense_impl = RS_DENSE_AUTO, maxsim_impl = RS_MAXSIM_AUTO;
   int last_dense_impl = 0, last_maxsim_impl = 0;
   int64_t launches = 0;
@@ -169,6 +175,7 @@ int rs_create(int device, rs_handle** out) {
     return rc;
   }
   h->tc5 = rs::tc5_create(device, h->num_sms);
+  h->comm = rs::comm_create(device, h->num_sms);
   *out = h;
   return RS_OK;
 }
@@ -178,6 +185,9 @@ int rs_destroy(rs_handle* h) {
   DeviceGuard guard(h->device);
   cudaDeviceSynchronize();
   if (h->tc5) rs::tc5_destroy(h->tc5);
+  if (h->comm) rs::comm_destroy(h->comm);
+  if (h->shard_scores) cudaFree(h->shard_scores);
+  if (h->shard_ids) cudaFree(h->shard_ids);
   if (h->ws_keys) cudaFree(h->ws_keys);
   if (h->ticket) cudaFree(h->ticket);
   if (h->unit_ctr) cudaFree(h->unit_ctr);
@@ -346,7 +356,7 @@ int rs_topk_merge(rs_handle* h, const float* scores, const int64_t* ids, int32_t
 // ------------------------------------------------------------------------------ MaxSim
 int rs_maxsim(rs_handle* h, const void* q, int32_t nq, int32_t lq, int32_t d, int32_t dtype, const float* q_weight,
               const void* doc_tokens, int64_t n_tokens, const int32_t* doc_offsets, int32_t nd, const int32_t* cand,
-              int32_t nc, float* out_scores, int32_t* out_argmax, void* stream) {
+              int32_t nc, float* out_scores, int32_t* out_argmax, float* out_tokmax, void* stream) {
   if (!h) return RS_ERR_INVALID_ARG;
   if (nq < 0 || nd < 0 || nc < 0) return fail(h, RS_ERR_INVALID_ARG, "rs_maxsim: negative size");
   const int ndo = cand ? nc : nd;
@@ -358,7 +368,7 @@ int rs_maxsim(rs_handle* h, const void* q, int32_t nq, int32_t lq, int32_t d, in
   DeviceGuard guard(h->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   order_after_last(h, st);
-  rs::MaxSimParams p{q, q_weight, doc_tokens, doc_offsets, cand, out_scores, out_argmax, n_tokens, nq, lq, d, nd, nc};
+  rs::MaxSimParams p{q, q_weight, doc_tokens, doc_offsets, cand, out_scores, out_argmax, out_tokmax, n_tokens, nq, lq, d, nd, nc};
 
   if (dtype == RS_F32) {
     if (h->maxsim_impl != RS_MAXSIM_AUTO && h->maxsim_impl != RS_MAXSIM_SIMT)
@@ -374,12 +384,13 @@ int rs_maxsim(rs_handle* h, const void* q, int32_t nq, int32_t lq, int32_t d, in
   if (h->maxsim_impl == RS_MAXSIM_SIMT) return fail(h, RS_ERR_UNSUPPORTED, "rs_maxsim: SIMT path takes fp32 inputs only");
   if (!aligned16(q) || !aligned16(doc_tokens)) return fail(h, RS_ERR_INVALID_ARG, "rs_maxsim: q and doc_tokens must be 16-byte aligned");
 
-  // Kernel family by shape: shared candidates with at least one full 128-row tile of query tokens -> the
-  // compute-bound tcgen05 kernel; per-query candidates (or too few query tokens) -> the document-streaming tcgen05
-  // kernel; argmax output or d outside {64, 128} -> the general mma.sync kernel.
+  // Kernel family by shape: shared candidates with at least one full 128-row tile of query tokens and d in
+  // {64, 128} -> the compute-bound tcgen05 kernel; per-query candidates, too few query tokens, d = 768 (any multiple
+  // of 64 up to 1024) or the arg-max / per-token-max outputs of the explanations path -> the document-streaming
+  // tcgen05 kernel; what is left (d % 64 != 0, query tiles too large for shared memory) -> the mma.sync kernel.
   int impl = h->maxsim_impl;
-  const bool tc5_ok = rs::tc5_maxsim_supported(h->tc5, nq, lq, d, nd, cand, out_argmax);
-  const bool cand_ok = rs::tc5_maxsim_cand_supported(h->tc5, nq, lq, d, nd, ndo, out_argmax);
+  const bool tc5_ok = rs::tc5_maxsim_supported(h->tc5, nq, lq, d, nd, cand, out_argmax) && out_tokmax == nullptr;
+  const bool cand_ok = rs::tc5_maxsim_cand_supported(h->tc5, nq, lq, d, nd, ndo);
   if (impl == RS_MAXSIM_AUTO) impl = tc5_ok ? RS_MAXSIM_TCGEN05 : (cand_ok ? RS_MAXSIM_TCGEN05_CAND : RS_MAXSIM_MMA);
   if (impl == RS_MAXSIM_TCGEN05) {
     if (!tc5_ok)
@@ -396,7 +407,8 @@ int rs_maxsim(rs_handle* h, const void* q, int32_t nq, int32_t lq, int32_t d, in
   }
   if (impl == RS_MAXSIM_TCGEN05_CAND) {
     if (!cand_ok)
-      return fail(h, RS_ERR_UNSUPPORTED, "rs_maxsim: candidate tcgen05 path needs no argmax, lq <= 128, d in {64,128}");
+      return fail(h, RS_ERR_UNSUPPORTED,
+                  "rs_maxsim: candidate tcgen05 path needs lq <= 128, d a multiple of 64 up to 1024 and lq_pad * d <= 24576");
     int launched = 0;
     std::string err;
     int rc = rs::tc5_maxsim_cand(h->tc5, p, dtype, st, &launched, &err);
@@ -462,6 +474,139 @@ int rs_filter_mask(rs_handle* h, const int32_t* const* cols, int32_t nclauses, c
   e = rs::launch_filter_mask(cols, nclauses, h->filt_dev + nclauses + 1, h->filt_dev, tombstone, n, out_mask, h->num_sms, st);
   if (e != cudaSuccess) return cuda_fail(h, e, "filter_mask_kernel launch");
   h->launches += 1;
+  return RS_OK;
+}
+
+// ------------------------------------------------------------------------------ multi-GPU exchange
+int rs_comm_export(rs_handle* h, int32_t world, int32_t rank, int64_t slot_bytes, void* out_handle) {
+  if (!h) return RS_ERR_INVALID_ARG;
+  if (!out_handle || slot_bytes < 0) return fail(h, RS_ERR_INVALID_ARG, "rs_comm_export: bad argument");
+  DeviceGuard guard(h->device);
+  std::string err;
+  const int rc = rs::comm_export(h->comm, world, rank, (size_t)slot_bytes, out_handle, &err);
+  if (rc != 0) return fail(h, rc, "rs_comm_export: %s", err.c_str());
+  return RS_OK;
+}
+
+int rs_comm_open(rs_handle* h, const void* handles) {
+  if (!h) return RS_ERR_INVALID_ARG;
+  if (!handles) return fail(h, RS_ERR_INVALID_ARG, "rs_comm_open: NULL handles");
+  DeviceGuard guard(h->device);
+  std::string err;
+  const int rc = rs::comm_open(h->comm, handles, &err);
+  if (rc != 0) return fail(h, rc, "rs_comm_open: %s", err.c_str());
+  return RS_OK;
+}
+
+int rs_comm_close(rs_handle* h) {
+  if (!h) return RS_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  cudaDeviceSynchronize();
+  rs::comm_close(h->comm);
+  return RS_OK;
+}
+
+int rs_comm_info(const rs_handle* h, int32_t* world, int32_t* rank, int64_t* slot_bytes) {
+  if (!h) return RS_ERR_INVALID_ARG;
+  const bool open = rs::comm_is_open(h->comm);
+  if (world) *world = open ? rs::comm_world(h->comm) : 0;
+  if (rank) *rank = open ? rs::comm_rank(h->comm) : 0;
+  if (slot_bytes) *slot_bytes = open ? (int64_t)rs::comm_slot_bytes(h->comm) : 0;
+  return RS_OK;
+}
+
+int rs_allgather_topk(rs_handle* h, const float* local_scores, const int64_t* local_ids, int32_t nq, int32_t k_in,
+                      int32_t k_out, float* out_scores, int64_t* out_ids, void* stream) {
+  if (!h) return RS_ERR_INVALID_ARG;
+  if (nq == 0) return RS_OK;
+  if (!local_scores || !local_ids || !out_scores || !out_ids || nq < 0 || k_in < 1 || k_out < 1)
+    return fail(h, RS_ERR_INVALID_ARG, "rs_allgather_topk: bad argument");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  order_after_last(h, st);
+  std::string err;
+  const int rc = rs::comm_allgather_topk(h->comm, local_scores, local_ids, nq, k_in, k_out, out_scores, out_ids, st, &err);
+  if (rc != 0) return fail(h, rc, "rs_allgather_topk: %s", err.c_str());
+  h->launches += 1;
+  return RS_OK;
+}
+
+int rs_allgather(rs_handle* h, const void* local, int64_t bytes, void* out, void* stream) {
+  if (!h) return RS_ERR_INVALID_ARG;
+  if (bytes == 0) return RS_OK;
+  if (!local || !out || bytes < 0) return fail(h, RS_ERR_INVALID_ARG, "rs_allgather: bad argument");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  order_after_last(h, st);
+  std::string err;
+  const int rc = rs::comm_allgather(h->comm, local, (size_t)bytes, out, st, &err);
+  if (rc != 0) return fail(h, rc, "rs_allgather: %s", err.c_str());
+  h->launches += 1;
+  return RS_OK;
+}
+
+int rs_allreduce_max_f32(rs_handle* h, const float* local, int64_t n, float* out, void* stream) {
+  if (!h) return RS_ERR_INVALID_ARG;
+  if (n == 0) return RS_OK;
+  if (!local || !out || n < 0) return fail(h, RS_ERR_INVALID_ARG, "rs_allreduce_max_f32: bad argument");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  order_after_last(h, st);
+  std::string err;
+  const int rc = rs::comm_allreduce_max(h->comm, local, (size_t)n, out, st, &err);
+  if (rc != 0) return fail(h, rc, "rs_allreduce_max_f32: %s", err.c_str());
+  h->launches += 1;
+  return RS_OK;
+}
+
+// One request against a row-sharded corpus, host buffers in and out: H2D(queries) -> local top-k -> ONE fused
+// push + merge kernel over peer memory writing the merged result into mapped pinned memory -> synchronise.
+int rs_dense_topk_sharded_host(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_t dtype, const float* inv_norm,
+                               int32_t metric, const void* queries_host, int32_t nq, const uint32_t* mask_dev,
+                               int64_t mask_stride_words, int32_t k, int64_t id_base, float* out_scores_host,
+                               int64_t* out_ids_host, void* stream) {
+  if (!h) return RS_ERR_INVALID_ARG;
+  if (nq < 0 || n < 0) return fail(h, RS_ERR_INVALID_ARG, "rs_dense_topk_sharded_host: negative size");
+  if (nq == 0) return RS_OK;
+  if (!queries_host || !out_scores_host || !out_ids_host) return fail(h, RS_ERR_INVALID_ARG, "rs_dense_topk_sharded_host: NULL host buffer");
+  if (d <= 0 || k < 1 || k > kMaxK) return fail(h, RS_ERR_INVALID_ARG, "rs_dense_topk_sharded_host: bad d/k");
+  if (!rs::comm_is_open(h->comm)) return fail(h, RS_ERR_INVALID_ARG, "rs_dense_topk_sharded_host: no exchange open (rs_comm_export + rs_comm_open)");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t q_bytes = align_up((size_t)nq * d * 2, 256);
+  const size_t os_bytes = align_up((size_t)nq * k * 4, 256);
+  const size_t oi_bytes = align_up((size_t)nq * k * 8, 256);
+  int rc = ensure_staging(h, q_bytes + os_bytes + oi_bytes, q_bytes);
+  if (rc != RS_OK) return rc;
+  const size_t pairs = (size_t)nq * k;
+  if (pairs > h->shard_pairs) {
+    if (h->shard_scores) cudaFree(h->shard_scores);
+    if (h->shard_ids) cudaFree(h->shard_ids);
+    h->shard_scores = nullptr;
+    h->shard_ids = nullptr;
+    h->shard_pairs = 0;
+    const size_t want = pairs < 4096 ? 4096 : pairs;
+    cudaError_t e = cudaMalloc(&h->shard_scores, want * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&h->shard_ids, want * sizeof(int64_t));
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaMalloc(shard top-k)");
+    h->shard_pairs = want;
+  }
+  uint8_t* hp = static_cast<uint8_t*>(h->pinned);
+  uint8_t* dp = static_cast<uint8_t*>(h->dev_stage);
+  memcpy(hp, queries_host, (size_t)nq * d * 2);
+  cudaError_t e = cudaMemcpyAsync(dp, hp, q_bytes, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return cuda_fail(h, e, "H2D(queries)");
+  rc = rs_dense_topk(h, corpus, n, d, dtype, inv_norm, metric, dp, nq, mask_dev, mask_stride_words, k, id_base,
+                     h->shard_scores, h->shard_ids, stream);
+  if (rc != RS_OK) return rc;
+  uint8_t* hp_dev = static_cast<uint8_t*>(h->pinned_dev);
+  rc = rs_allgather_topk(h, h->shard_scores, h->shard_ids, nq, k, k, reinterpret_cast<float*>(hp_dev + q_bytes),
+                         reinterpret_cast<int64_t*>(hp_dev + q_bytes + os_bytes), stream);
+  if (rc != RS_OK) return rc;
+  e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(h, e, "rs_dense_topk_sharded_host: stream synchronize");
+  memcpy(out_scores_host, hp + q_bytes, (size_t)nq * k * 4);
+  memcpy(out_ids_host, hp + q_bytes + os_bytes, (size_t)nq * k * 8);
   return RS_OK;
 }
 

@@ -22,7 +22,7 @@ int tc5_maxsim(Tc5State* s, const MaxSimParams& p, int dtype, cudaStream_t strea
 
 // Per-query-candidate MaxSim (reference rerank shape, rerankers.py:351-385); also serves shared candidates when
 // there are too few query tokens for the kernel above (cand == null: candidate j of every query is document j).
-bool tc5_maxsim_cand_supported(const Tc5State* s, int nq, int lq, int d, int nd, int nc, const int32_t* out_argmax);
+bool tc5_maxsim_cand_supported(const Tc5State* s, int nq, int lq, int d, int nd, int nc);
 int tc5_maxsim_cand(Tc5State* s, const MaxSimParams& p, int dtype, cudaStream_t stream, int* launched, std::string* err);
 
 // shared helpers (defined in maxsim_tc5.cu)

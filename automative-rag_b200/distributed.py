@@ -1,5 +1,11 @@
 """Multi-GPU sharding of the two stages: one process per GPU, `torch.distributed`
-(NCCL over NVLink/NVSwitch) for the plumbing, ONE all-gather per stage.
+for the plumbing (rendezvous, handle exchange, barriers), ONE exchange step per stage.
+
+The exchange itself is the engine's own kernel over NVLink peer memory whenever the engine has an
+open exchange (`Engine.comm_init(group)`; `rs_allgather_topk` = push + flag + k-way merge fused in
+one launch, `rs_allgather`, `rs_allreduce_max_f32`): no NCCL call and no torch op sits between the
+local scoring kernel and the merged result.  Without it (gloo on CPU in the tests, or before
+`comm_init`) the same steps run as `all_gather_into_tensor` + `rs_topk_merge`.
 
 Dense: the corpus is row-partitioned (contiguous block per rank, global id = shard offset + local
 row; the filter mask is partitioned the same way); every rank holds every query, runs its local
@@ -76,6 +82,9 @@ class ShardedDenseIndex:
         self._local_search = local_search or self._engine_search
         self._merge = merge or self._engine_merge
         self._wire: Optional[torch.Tensor] = None
+        # the engine's own exchange over peer memory, when it spans exactly this group
+        self._peer = (local_search is None and merge is None and engine is not None and self.world > 1
+                      and engine.comm_world == self.world)
 
     def _engine_search(self, queries, k, mask, out_scores, out_ids):
         self.engine.dense_topk(self.corpus, queries, k, mask=mask, inv_norm=self.inv_norm, metric=self.metric,
@@ -98,6 +107,8 @@ class ShardedDenseIndex:
         self._local_search(queries, k, mask, scores, ids)
         if self.world == 1:
             return scores, ids
+        if self._peer:  # push to every peer + flag + merge, one launch
+            return self.engine.allgather_topk(scores, ids, k)
         gathered = all_gather_topk(self._wire, self.group)
         g_scores, g_ids = gathered_views(gathered, self.world, nq, k)
         return self._merge(g_scores, g_ids, k)
@@ -113,6 +124,7 @@ class ShardedMaxSim:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._local_score = local_score or (lambda q, w: self.engine.maxsim(q, self.tokens, self.offsets, q_weight=w))
+        self._peer = local_score is None and engine is not None and self.world > 1 and engine.comm_world == self.world
 
     def scores(self, q: torch.Tensor, q_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
         """[nq, nd_total] fp32 on every rank, columns in global document order."""
@@ -121,11 +133,18 @@ class ShardedMaxSim:
             return local
         nq = local.shape[0]
         per = (self.nd_total + self.world - 1) // self.world  # pad every rank's block to the largest
-        send = torch.full((nq, per), float("-inf"), dtype=torch.float32, device=local.device)
-        send[:, : local.shape[1]] = local
-        out = torch.empty(self.world * nq * per, dtype=torch.float32, device=local.device)
-        dist.all_gather_into_tensor(out, send.reshape(-1), group=self.group)
-        blocks = out.view(self.world, nq, per)
+        per = (per + 3) // 4 * 4                               # ... and to whole 16-byte units
+        if local.shape[1] == per:
+            send = local
+        else:
+            send = torch.full((nq, per), float("-inf"), dtype=torch.float32, device=local.device)
+            send[:, : local.shape[1]] = local
+        if self._peer:
+            blocks = self.engine.allgather(send)               # [G, nq, per], the engine's own exchange kernel
+        else:
+            out = torch.empty(self.world * nq * per, dtype=torch.float32, device=local.device)
+            dist.all_gather_into_tensor(out, send.reshape(-1), group=self.group)
+            blocks = out.view(self.world, nq, per)
         cols = []
         for r in range(self.world):
             lo, hi = shard_bounds(self.nd_total, self.world, r)
@@ -151,11 +170,21 @@ def partition_candidates(cand: torch.Tensor, world_size: int, rank: int) -> Tupl
     return slots, loc_cand
 
 
+def owned_candidates(cand: torch.Tensor, world_size: int, rank: int) -> torch.Tensor:
+    """Per-query candidate lists `cand` [nq, nc] of GLOBAL document ids (documents owned round-robin: owner =
+    id % world_size, local index = id // world_size) -> int32 [nq, nc] local indices for `rs_maxsim`, -1 where the
+    candidate belongs to another rank or is padding (-1 upstream): an index outside the collection is an empty
+    document, which the kernel skips and scores -inf.  Element-wise, no host synchronisation."""
+    mine = (cand >= 0) & ((cand % world_size) == rank)
+    loc = torch.div(cand, world_size, rounding_mode="floor")
+    return torch.where(mine, loc, torch.full_like(loc, -1)).to(torch.int32).contiguous()
+
+
 class ShardedCandidateMaxSim:
     """Retrieve-then-rerank shape (BASELINE config 4b / stage 2 of config 5): every query has its own candidate
     list; a candidate's token embeddings live on the rank that owns the document (id % G).  Each rank scores the
-    candidates it owns, ONE all-gather of the [nq, nc] score blocks, element-wise max (every candidate has exactly
-    one owner, all other ranks contribute -inf)."""
+    candidates it owns (the others are -1 = empty documents the kernel skips), ONE exchange of the [nq, nc] score
+    blocks as an element-wise max (every candidate has exactly one owner, all other ranks contribute -inf)."""
 
     def __init__(self, local_tokens: torch.Tensor, local_offsets: torch.Tensor, *, engine=None, group=None,
                  local_score: Optional[Callable] = None):
@@ -165,16 +194,16 @@ class ShardedCandidateMaxSim:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._local_score = local_score or (
             lambda q, loc_cand, w: self.engine.maxsim(q, self.tokens, self.offsets, q_weight=w, cand=loc_cand))
+        self._peer = local_score is None and engine is not None and self.world > 1 and engine.comm_world == self.world
 
     def scores(self, q: torch.Tensor, cand: torch.Tensor, q_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """[nq, nc] fp32 on every rank, column j = score of cand[:, j]."""
+        """[nq, nc] fp32 on every rank, column j = score of cand[:, j] (-inf for padding ids)."""
         nq, nc = cand.shape
-        slots, loc_cand = partition_candidates(cand, self.world, self.rank)
-        full = torch.full((nq, nc), float("-inf"), dtype=torch.float32, device=cand.device)
-        if slots.shape[1]:
-            full.scatter_(1, slots, self._local_score(q, loc_cand, q_weight))
+        local = self._local_score(q, owned_candidates(cand, self.world, self.rank), q_weight)  # -inf where not owned
         if self.world == 1:
-            return full
+            return local
+        if self._peer:
+            return self.engine.allreduce_max(local)
         out = torch.empty(self.world * nq * nc, dtype=torch.float32, device=cand.device)
-        dist.all_gather_into_tensor(out, full.reshape(-1), group=self.group)
+        dist.all_gather_into_tensor(out, local.reshape(-1).contiguous(), group=self.group)
         return out.view(self.world, nq, nc).max(dim=0).values

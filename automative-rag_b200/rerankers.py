@@ -140,7 +140,7 @@ class B200ColBERTReranker:
 
     # -- the hot path -------------------------------------------------------------------------
     def _maxsim_device(self, query_embeddings: torch.Tensor, doc_embeddings_list: Sequence[torch.Tensor],
-                       q_weight: Optional[torch.Tensor] = None, want_argmax: bool = False):
+                       q_weight: Optional[torch.Tensor] = None, want_argmax: bool = False, want_tokmax: bool = False):
         q = query_embeddings
         if q.dim() == 2:
             q = q.unsqueeze(0)
@@ -149,7 +149,7 @@ class B200ColBERTReranker:
         tokens, offs = pack_documents(doc_embeddings_list, dev, self.compute_dtype)
         if q_weight is not None:
             q_weight = q_weight.to(device=dev, dtype=torch.float32).reshape(q.shape[0], q.shape[1]).contiguous()
-        return self.engine.maxsim(q, tokens, offs, q_weight=q_weight, want_argmax=want_argmax)
+        return self.engine.maxsim(q, tokens, offs, q_weight=q_weight, want_argmax=want_argmax, want_tokmax=want_tokmax)
 
     def _compute_maxsim_scores(self, query_embeddings: torch.Tensor,
                                doc_embeddings_list: List[torch.Tensor]) -> List[float]:
@@ -250,19 +250,18 @@ class B200ColBERTReranker:
         weight = torch.tensor([[1.0 if (m == 1 and t not in ("[CLS]", "[SEP]")) else 0.0
                                 for m, t in zip(q_mask[:lq], q_tokens[:lq])]], dtype=torch.float32)
         doc_embeddings_list = self._encode_documents_batched(documents)
-        scores, argmax = self._maxsim_device(query_embeddings, doc_embeddings_list, q_weight=weight, want_argmax=True)
-        # per-query-token maxima for the explanation strings: one more call with one-hot weights is
-        # avoided by recomputing the few needed dot products on the device
-        q_dev = query_embeddings.reshape(lq, -1).to(self.engine.device, torch.float32)
+        # one rs_maxsim call: scores, the arg-max document token per query token (:492) and the maximum itself — the
+        # "similarity" of an explanation (:493-501) — all out of the kernel's TMEM epilogue
+        scores, argmax, tokmax = self._maxsim_device(query_embeddings, doc_embeddings_list, q_weight=weight,
+                                                     want_argmax=True, want_tokmax=True)
+        argmax_h, tokmax_h = argmax[0].tolist(), tokmax[0].tolist()
         results = []
         for j, doc in enumerate(documents):
             d_enc = tok([doc.page_content], add_special_tokens=True, max_length=self.max_doc_length,
                         padding="max_length", truncation=True, return_tensors="pt")
             d_tokens = tok.convert_ids_to_tokens(d_enc.input_ids[0].tolist())
             d_mask = d_enc.attention_mask[0].tolist()
-            idx = argmax[0, j].tolist()
-            d_dev = doc_embeddings_list[j].to(self.engine.device, torch.float32)
-            sims = (q_dev * d_dev[torch.tensor(idx, device=d_dev.device)]).sum(dim=1).tolist()
+            idx, sims = argmax_h[j], tokmax_h[j]
             explanations = []
             for qidx in range(min(lq, len(q_tokens))):
                 if (q_mask[qidx] == 0 or q_tokens[qidx] in ("[PAD]", "[CLS]", "[SEP]", "[UNK]")

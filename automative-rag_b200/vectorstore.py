@@ -21,7 +21,9 @@ the mask fused, top-k in-kernel) -> k (score, id) pairs come back.  No CPU scori
 """
 from __future__ import annotations
 
+import json
 import logging
+import os
 import time
 import uuid
 from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
@@ -38,6 +40,7 @@ logger = logging.getLogger(__name__)
 # Fields indexed by the reference (vectorstore.py:93-103) and their schema (:110-113).
 KEYWORD_FIELDS = ("manufacturer", "model", "category", "engine_type", "transmission", "source", "source_id")
 INTEGER_FIELDS = ("year", "ingestion_time")
+MAX_K = 2048  # rs_dense_topk: 1 <= k <= 2048
 
 
 class Collection:
@@ -56,6 +59,10 @@ class Collection:
         self.columns: Dict[str, torch.Tensor] = {f: torch.empty(0, dtype=torch.int32, device=self.device)
                                                  for f in KEYWORD_FIELDS + INTEGER_FIELDS}
         self.keyword_dicts: Dict[str, Dict[str, int]] = {f: {} for f in KEYWORD_FIELDS}
+        self.int_fields: List[str] = list(INTEGER_FIELDS)   # + integer columns created lazily for un-indexed keys
+        # fields that hold a value the int32 column cannot express (a list-valued keyword, which Qdrant matches on any
+        # element; a numeric string ...): filters on them are evaluated on the host payloads instead
+        self.unencodable: Dict[str, bool] = {}
         self.tombstone = torch.empty(0, dtype=torch.int32, device=self.device)
         self.ids: List[str] = []
         self.id_to_row: Dict[str, int] = {}
@@ -85,20 +92,48 @@ class Collection:
         self.tombstone = grow(self.tombstone, (cap // 32,), fill=0)
         self.capacity = cap
 
-    def _encode_fields(self, metadata: Dict[str, Any]) -> Dict[str, int]:
-        row: Dict[str, int] = {}
-        for f in KEYWORD_FIELDS:
-            v = metadata.get(f)
+    def _encode_value(self, f: str, v: Any) -> int:
+        """int32 code of payload value `v` of field `f`.  A value the column cannot express marks the field, so that
+        filters on it fall back to the host evaluator (the compiled path must never disagree with it)."""
+        if f in self.keyword_dicts:
             if isinstance(v, str):
                 d = self.keyword_dicts[f]
-                row[f] = d.setdefault(v, len(d))
-            else:
-                row[f] = -1
-        for f in INTEGER_FIELDS:
-            v = metadata.get(f)
-            ok = isinstance(v, int) and not isinstance(v, bool) and -(2**31) < v < 2**31
-            row[f] = int(v) if ok else INT_MISSING
-        return row
+                return d.setdefault(v, len(d))
+            if v is not None:
+                self.unencodable[f] = True  # list-valued keyword, number in a keyword field ...
+            return -1
+        if isinstance(v, bool) or v is None:  # a bool never matches an integer condition (payload_passes)
+            return INT_MISSING
+        if isinstance(v, int) and -(2**31) < v < 2**31:
+            return int(v)
+        if isinstance(v, float) and v.is_integer() and abs(v) < 2**31:
+            return int(v)  # 2020.0 matches MatchValue(2020) and Range(2020, 2020) on the host path too
+        self.unencodable[f] = True
+        return INT_MISSING
+
+    def _encode_fields(self, metadata: Dict[str, Any]) -> Dict[str, int]:
+        return {f: self._encode_value(f, metadata.get(f)) for f in self.columns}
+
+    def ensure_column(self, field: str) -> bool:
+        """Create (once) the device column of a payload key the reference does not index — `custom_filters` of the
+        API (query_models.py:22-28) reach the store as ordinary metadata keys.  The type is taken from the stored
+        values: all strings -> keyword (dictionary-encoded), all integers -> integer.  Returns False when the values
+        are mixed or neither, in which case filters on the key stay on the host evaluator."""
+        if field in self.columns:
+            return True
+        vals = [(p.get("metadata", {}) or {}).get(field) for p in self.payloads]
+        present = [v for v in vals if v is not None]
+        if present and all(isinstance(v, str) for v in present):
+            self.keyword_dicts[field] = {}
+        elif present and all(isinstance(v, int) and not isinstance(v, bool) for v in present):
+            self.int_fields.append(field)
+        else:
+            return False
+        col = torch.full((self.capacity,), INT_MISSING, dtype=torch.int32, device=self.device)
+        self.columns[field] = col
+        if vals:
+            col[: self.n] = torch.tensor([self._encode_value(field, v) for v in vals], dtype=torch.int32, device=self.device)
+        return True
 
     def upsert(self, ids: Sequence[str], vectors: torch.Tensor, payloads: Sequence[Dict[str, Any]]) -> None:
         """vectors: float32 [m, d] on any device."""
@@ -131,7 +166,8 @@ class Collection:
     def rebuild_columns(self) -> List[str]:
         """Re-encode every stored payload into fresh payload columns and keyword dictionaries — the counterpart of
         dropping and recreating Qdrant's payload indexes (vectorstore.py:412-470).  Returns the rebuilt fields."""
-        self.keyword_dicts = {f: {} for f in KEYWORD_FIELDS}
+        self.keyword_dicts = {f: {} for f in self.keyword_dicts}
+        self.unencodable = {}
         cols: Dict[str, List[int]] = {f: [] for f in self.columns}
         for p in self.payloads:
             for f, val in self._encode_fields(p.get("metadata", {}) or {}).items():
@@ -167,13 +203,97 @@ class Collection:
         tomb = self.tombstone[: (self.n + 31) // 32] if self.deleted else None
         if flt is None:
             return self.engine.filter_mask([], [], self.n, tombstone=tomb)
+        for key in _filter_keys(flt):  # un-indexed payload keys get their column on first use
+            if key.startswith("metadata."):
+                self.ensure_column(key[len("metadata."):])
         try:
-            clauses = compile_filter(flt, self.keyword_dicts, INTEGER_FIELDS)
-        except UnsupportedFilter:
+            clauses = compile_filter(flt, self.keyword_dicts, self.int_fields)
+            if any(self.unencodable.get(name) for name, _ in clauses):
+                raise UnsupportedFilter("a filtered field holds values the device column cannot express")
+        except UnsupportedFilter as e:
+            logger.warning(f"filter evaluated on the host payloads ({e})")
             return self._host_mask(flt, tomb)
         cols = [self.columns[name][: self.n] for name, _ in clauses]
         sets = [vals for _, vals in clauses]
         return self.engine.filter_mask(cols, sets, self.n, tombstone=tomb)
+
+    def matching_rows(self, flt: Optional[Filter], limit: int) -> List[int]:
+        """Row indices (insertion order) of the first `limit` live rows that pass `flt`: the mask is built on the
+        device, its set bits are listed on the device, `limit` integers come back."""
+        if self.n == 0 or limit <= 0:
+            return []
+        mask = self.device_mask(flt)
+        if mask is None:
+            return list(range(min(self.n, limit)))
+        bits = (mask.view(-1, 1) >> torch.arange(32, device=mask.device, dtype=torch.int32)) & 1
+        rows = torch.nonzero(bits.view(-1)[: self.n], as_tuple=False).view(-1)[:limit]
+        return rows.tolist()
+
+    # -- persistence (the reference keeps its vectors in Qdrant's storage volume, docker-compose.yml:229-230) -----
+    def save(self, path: str) -> None:
+        """Write the collection to directory `path`: vectors (row-major, as stored), 1/|row|, the int32 payload
+        columns, tombstone words — one device-to-host copy per array (in 1 GiB pieces) — plus ids, payloads and the
+        keyword dictionaries as JSON."""
+        os.makedirs(path, exist_ok=True)
+
+        def dump(t: torch.Tensor, name: str) -> None:
+            flat = t.contiguous().view(-1)
+            step = max(1, (1 << 30) // max(flat.element_size(), 1))
+            with open(os.path.join(path, name), "wb") as f:
+                for a in range(0, flat.numel(), step):
+                    f.write(flat[a: a + step].cpu().view(torch.uint8).numpy().tobytes())
+
+        n = self.n
+        dump(self.vectors[:n], "vectors.bin")
+        dump(self.inv_norm[:n], "inv_norm.bin")
+        dump(self.tombstone[: (n + 31) // 32], "tombstone.bin")
+        for f, col in self.columns.items():
+            dump(col[:n], f"column.{f}.bin")
+        meta = {"format": 1, "name": self.name, "dim": self.dim, "dtype": str(self.dtype).replace("torch.", ""),
+                "distance": self.distance, "n": n, "deleted": self.deleted, "fields": list(self.columns),
+                "int_fields": self.int_fields, "keyword_dicts": self.keyword_dicts, "unencodable": self.unencodable,
+                "ids": self.ids}
+        with open(os.path.join(path, "payloads.json"), "w") as f:
+            json.dump(self.payloads, f)
+        with open(os.path.join(path, "meta.json"), "w") as f:  # written last: a directory without it is incomplete
+            json.dump(meta, f)
+
+    @classmethod
+    def load(cls, path: str, engine: _ffi.Engine) -> "Collection":
+        """Rebuild a collection saved by `save` on `engine`'s GPU: one host-to-device copy per array."""
+        import numpy as np
+
+        with open(os.path.join(path, "meta.json")) as f:
+            meta = json.load(f)
+        if meta.get("format") != 1:
+            raise ValueError(f"unknown collection format {meta.get('format')!r} in {path}")
+        dtype = getattr(torch, meta["dtype"])
+        n = meta["n"]
+        col = cls(meta["name"], meta["dim"], engine, dtype=dtype, distance=meta["distance"], capacity=max(n, 1))
+        col.int_fields = list(meta["int_fields"])
+        col.keyword_dicts = {f: dict(d) for f, d in meta["keyword_dicts"].items()}
+        col.unencodable = dict(meta.get("unencodable", {}))
+
+        def read(name: str, dt: torch.dtype, shape) -> torch.Tensor:
+            raw = np.fromfile(os.path.join(path, name), dtype=np.uint8)
+            return torch.from_numpy(raw).view(dt).view(shape).to(col.device)
+
+        col.vectors[:n] = read("vectors.bin", dtype, (n, meta["dim"]))
+        col.inv_norm[:n] = read("inv_norm.bin", torch.float32, (n,))
+        col.tombstone[: (n + 31) // 32] = read("tombstone.bin", torch.int32, ((n + 31) // 32,))
+        for f in meta["fields"]:
+            if f not in col.columns:
+                col.columns[f] = torch.full((col.capacity,), INT_MISSING, dtype=torch.int32, device=col.device)
+            col.columns[f][:n] = read(f"column.{f}.bin", torch.int32, (n,))
+        with open(os.path.join(path, "payloads.json")) as f:
+            col.payloads = json.load(f)
+        col.ids = list(meta["ids"])
+        col.n, col.deleted = n, meta["deleted"]
+        tomb = col.tombstone[: (n + 31) // 32].cpu().numpy().view(np.uint32) if col.deleted else None
+        for row, pid in enumerate(col.ids):  # a re-upserted id maps to its newest, live row
+            if tomb is None or not (int(tomb[row >> 5]) >> (row & 31)) & 1:
+                col.id_to_row[pid] = row
+        return col
 
     def _host_mask(self, flt: Filter, tomb: Optional[torch.Tensor]) -> torch.Tensor:
         """Filters on un-indexed payload keys: evaluate on the host payloads, upload the bits."""
@@ -193,6 +313,15 @@ def _lookup(payload: Dict[str, Any], dotted: str) -> Any:
             return None
         cur = cur[part]
     return cur
+
+
+def _filter_keys(flt: Union[Filter, FieldCondition]) -> List[str]:
+    if isinstance(flt, FieldCondition):
+        return [flt.key]
+    out: List[str] = []
+    for c in (flt.must or []) + (flt.should or []):
+        out.extend(_filter_keys(c))
+    return out
 
 
 def payload_passes(payload: Dict[str, Any], flt: Union[Filter, FieldCondition]) -> bool:
@@ -247,6 +376,23 @@ class B200Client:
 
     def delete_collection(self, name: str) -> None:
         self.collections.pop(name, None)
+
+    def save(self, path: str) -> None:
+        """Persist every collection under directory `path` (one sub-directory each)."""
+        os.makedirs(path, exist_ok=True)
+        for i, (name, col) in enumerate(self.collections.items()):
+            col.save(os.path.join(path, f"collection-{i}"))
+
+    def load(self, path: str) -> List[str]:
+        """Load every collection found under `path`; returns their names."""
+        names = []
+        for sub in sorted(os.listdir(path)):
+            d = os.path.join(path, sub)
+            if os.path.exists(os.path.join(d, "meta.json")):
+                col = Collection.load(d, self.engine)
+                self.collections[col.name] = col
+                names.append(col.name)
+        return names
 
 
 class B200VectorStore:
@@ -331,8 +477,10 @@ class B200VectorStore:
         if qvec.numel() != col.dim:
             raise ValueError(f"query embedding has {qvec.numel()} dims, collection has {col.dim}")
         mask = col.device_mask(flt)
+        if k > MAX_K:  # never truncate silently (the reference has no such limit; deployed k is 20-40)
+            logger.warning(f"similarity search asked for k={k}; the scan kernel returns at most {MAX_K} results")
         scores, ids = col.engine.dense_topk_host(
-            col.vectors[: col.n], qvec.to(col.dtype).contiguous(), min(k, 2048), mask_dev=mask,
+            col.vectors[: col.n], qvec.to(col.dtype).contiguous(), min(k, MAX_K), mask_dev=mask,
             inv_norm=col.inv_norm[: col.n], metric=_ffi.RS_METRIC_COSINE)
         out: List[Tuple[Document, float]] = []
         for s, i in zip(scores[0].tolist(), ids[0].tolist()):
@@ -352,12 +500,9 @@ class B200VectorStore:
         try:
             col = self.collection
             documents: List[Document] = []
-            for pid, row in col.id_to_row.items():  # insertion order == scroll order
+            for row in col.matching_rows(filter_obj, limit):  # mask and row list built on the device; insertion order
                 p = col.payloads[row]
-                if payload_passes(p, filter_obj):
-                    documents.append(Document(page_content=p.get("page_content", ""), metadata=p.get("metadata", {})))
-                    if len(documents) >= limit:
-                        break
+                documents.append(Document(page_content=p.get("page_content", ""), metadata=p.get("metadata", {})))
             return documents
         except Exception as e:
             logger.error(f"Error in metadata search: {str(e)}")
@@ -408,6 +553,16 @@ class B200VectorStore:
             logger.error(error_msg)
             results["errors"].append(error_msg)
         return results
+
+    def save(self, path: str) -> None:
+        """Persist this store's collection (vectors, payload columns, tombstones, payloads) to directory `path`."""
+        self.collection.save(path)
+
+    def load(self, path: str) -> None:
+        """Replace this store's collection by the one saved at `path`."""
+        col = Collection.load(path, self.client.engine)
+        col.name = self.collection_name
+        self.client.collections[self.collection_name] = col
 
     # vectorstore.py:390-411
     def get_embedding(self, id: str) -> Optional[List[float]]:

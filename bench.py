@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""bench.py — queries/sec of the dense top-k hot path (BASELINE.json config 2) on N B200s.
+"""bench.py — queries/sec of the dense top-k hot path (BASELINE.json config 2) on N B200s, plus the north-star
+workloads (sharded MaxSim config 4a / 4b, the end-to-end config 5, a strong-scaled 12.5M-row scan) at every N.
 
-Workload (config.workload = "config2"): exact cosine top-10 over a 1M x 1024 fp16 corpus (rows
+Headline workload (config.workload = "config2"): exact cosine top-10 over a 1M x 1024 fp16 corpus (rows
 L2-normalised in fp32 then rounded, seed 1), SINGLE-QUERY searches, metadata-filter bitmask passed
 (p = 1.0: every bit set, so the mask words are read and tested but no row is skipped).
 
@@ -9,24 +10,31 @@ A step = one batch of `--queries-per-step` (default 64) independent single-query
 query is its own nq=1 scan launch that re-reads its whole shard from HBM (the corpus, 2 GB, is 16x
 the 126 MB L2, so nothing is cached between queries).  With N > 1 (torchrun, one process per GPU)
 the corpus is row-sharded (strong scaling: 1M rows total), every rank scans its shard for all
-queries of the step, ONE NCCL all-gather moves the step's k (id, score) pairs and one merge launch
-produces the global top-k on every rank.
+queries of the step, and ONE exchange kernel over NVLink peer memory (rs_allgather_topk: push to every peer +
+flag + k-way merge, comm.cu) leaves the global top-k on every rank.
 
   value     queries/s, inputs resident in HBM, CUDA events, max over ranks
-  e2e       the same metric through the public host entry point (rs_dense_topk_host at N = 1, the sharded index
-            at N > 1): the step's queries start in pinned host memory, its (score, id) pairs end in host memory,
-            H2D + D2H + synchronise inside the timed region once per step; e2e.per_request is the same with one
-            call, copy pair and synchronise per query (one request in flight)
+  e2e       the same metric through the public host entry point (rs_dense_topk_host at N = 1,
+            rs_dense_topk_sharded_host at N > 1): the step's queries start in pinned host memory, its (score, id)
+            pairs end in host memory, H2D + D2H + synchronise inside the timed region once per step;
+            e2e.per_request is the same with one call, copy pair and synchronise per query (one request in flight)
   roofline  dense_scan_kernel: algorithmic bytes per launch / average launch duration (events over
             the timed region / launches) vs MEASURED_PEAKS.json hbm_gbs
+  extra     N = 1 only: masked scans, k = 100 / 1000, config 3 (batched tcgen05), config 1 (the reference's call shape);
+            every N: config 4a / 4b with the candidates sharded by rank, config 5 weak-scaled (12.5M rows per GPU,
+            top-1000 -> exchange -> MaxSim over the winners -> top-10) with the SURVEY §8d parity block run in the
+            same process (returned scores recomputed on the CPU, threshold check on >= 1M sampled rows per shard,
+            full oracle on a 1M-row slice per shard, oracle MaxSim + stable rerank of the winners), and a
+            strong-scaled 12.5M-row scan
   cpu_baseline / --impl reference
             the reference's CPU scoring for this path — the numpy restatement of qdrant-client local
-            mode (oracle/dense.py; the arithmetic is third-party and absent from /root/reference) —
-            on the same corpus and queries, all host threads numpy's BLAS uses, bounded sample.
+            mode (oracle/dense.py; the arithmetic is third-party and absent from /root/reference; PARITY
+            UNPINNED) — on the same corpus and queries, all host threads, bounded sample.
 """
 from __future__ import annotations
 
 import argparse
+import datetime
 import json
 import os
 import statistics
@@ -58,10 +66,42 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=N_ROWS, help="total corpus rows (default: config 2)")
     ap.add_argument("--k", type=int, default=TOPK)
     ap.add_argument("--mask-p", type=float, default=1.0, help="Bernoulli pass probability of the filter mask")
-    ap.add_argument("--no-extra", action="store_true", help="skip the secondary (MaxSim / masked) measurements")
+    ap.add_argument("--no-extra", action="store_true", help="skip every secondary measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-queries", type=int, default=0, help="queries in the CPU sample (0 = auto, ~10-30 s)")
+    ap.add_argument("--c5-rows-per-gpu", type=int, default=12_500_000, help="config 5: corpus rows per GPU (weak scaling)")
+    ap.add_argument("--c5-pool-docs-per-gpu", type=int, default=125_000, help="config 5: candidate-token pool documents per GPU")
+    ap.add_argument("--c5-queries", type=int, default=16)
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity block of config 5")
     return ap.parse_args()
+
+
+def config_dict(args, world: int) -> dict:
+    """config of the JSON line — identical for the GPU arm and the reference arm at the same N."""
+    rows_local = (args.rows + world - 1) // world
+    return {"workload": "config2", "rows": args.rows, "rows_per_gpu": rows_local, "dim": DIM, "k": args.k,
+            "mask_p": args.mask_p, "queries_per_step": args.queries_per_step, "parallelism": f"row-shard x{world}",
+            "l2": (f"inputs larger than L2: every query re-reads its {rows_local * DIM * 2 / 1e6:.0f} MB shard "
+                   "(126 MB L2, loads carry an evict_first hint)")}
+
+
+def set_host_threads() -> int:
+    """Use every host core for the CPU arm whatever the launcher put into OMP_NUM_THREADS (torchrun sets it to 1,
+    which starved the reference arm at N > 1 in round 1).  Returns the thread count actually in use."""
+    import torch
+
+    n = int(os.environ.get("BENCH_CPU_THREADS", "0")) or (os.cpu_count() or 1)
+    torch.set_num_threads(n)
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+
+        threadpool_limits(limits=n)
+        used = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
+        if used:
+            n = max(used)
+    except Exception:  # noqa: BLE001
+        pass
+    return n
 
 
 # ------------------------------------------------------------------------------------------ data
@@ -167,13 +207,14 @@ def cpu_reference_qps(c32, queries_host, mask_bits, k: int, n_queries: int):
 
 def run_reference(args):
     """--impl reference: the reference's own CPU path for this metric (see module docstring)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return 0
     import numpy as np
     import torch
 
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return 0
-    threads = torch.get_num_threads()
+    threads = set_host_threads()
     dev = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
     corpus = make_corpus(0, args.rows, dev).cpu().numpy()
     queries = make_queries(args.queries_per_step).numpy().astype(np.float32)
@@ -195,11 +236,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config2", "rows": args.rows, "dim": DIM, "k": args.k, "mask_p": args.mask_p,
-                   "queries_per_step": args.queries_per_step, "sampled_queries_per_step": per_step},
+        "config": config_dict(args, max(world, args.gpus, 1)),
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{per_step} full-corpus queries per step x {args.steps} steps (numpy restatement "
-                                   "of qdrant-client local mode; fp16 corpus upcast to fp32 once, untimed)"},
+                         "sample": f"{per_step} full-corpus queries of the workload per step x {args.steps} steps (numpy "
+                                   "restatement of qdrant-client local mode, oracle/dense.py — parity unpinned; fp16 corpus "
+                                   "upcast to fp32 once, untimed)"},
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -208,25 +249,102 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+class Ctx:
+    """What every measurement needs: ranks, device, engine, peaks, timing helpers."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        import automative_rag_b200 as rag
+
+        self.args = args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=300))
+        self.eng = rag.get_engine(self.local_rank)
+        self.exchange = "single GPU"
+        if self.world > 1:
+            try:
+                self.eng.comm_init(slot_bytes=8 << 20)
+                self.exchange = "peer memory (rs_allgather_topk / rs_allreduce_max_f32 / rs_allgather, comm.cu)"
+            except Exception as e:  # noqa: BLE001 — e.g. CUDA IPC unavailable in this container: NCCL plumbing instead
+                log(f"rank {self.rank}: peer exchange unavailable ({e}); falling back to NCCL all-gather + rs_topk_merge")
+                self.exchange = f"NCCL all_gather + rs_topk_merge (peer exchange unavailable: {e})"
+            flag = torch.tensor([self.eng.comm_world], device=self.dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) != self.world and self.eng.comm_world:
+                self.eng.comm_close()  # all ranks or none
+        self.peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                self.peaks = json.load(f)
+        except Exception:  # noqa: BLE001
+            pass
+        self.hbm_peak, self.peak_src = (self.peaks["hbm_gbs"], "measured") if "hbm_gbs" in self.peaks else (6650.0, "fallback")
+        self.tf_burst = self.peaks.get("bf16_tflops", 1590.0)
+        self.tf_sustained = self.peaks.get("bf16_tflops_sustained", 1400.0)
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, v: float) -> float:
+        import torch
+        import torch.distributed as dist
+
+        if self.world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ok(self, ok: bool) -> bool:
+        import torch
+        import torch.distributed as dist
+
+        if self.world == 1:
+            return bool(ok)
+        t = torch.tensor([1 if ok else 0], device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def timed(self, fn, iters, warm=3):
+        """ms per call: CUDA events on the current stream, barrier + synchronise on both sides, max over ranks."""
+        import torch
+
+        for _ in range(warm):
+            fn()
+        self.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        self.barrier()
+        return self.max_over_ranks(a.elapsed_time(b) / iters)
+
+
 def run_b200(args):
     import numpy as np
     import torch
     import torch.distributed as dist
 
-    import automative_rag_b200 as rag
     from automative_rag_b200 import _ffi
     from automative_rag_b200.distributed import ShardedDenseIndex, shard_bounds
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    eng = rag.get_engine(local_rank)
+    cx = Ctx(args)
+    world, rank, dev, eng = cx.world, cx.rank, cx.dev, cx.eng
     eng.set_dense_impl(_ffi.RS_DENSE_SCAN)
 
     nq, k = args.queries_per_step, args.k
@@ -242,44 +360,35 @@ def run_b200(args):
     def step_device():
         return index.search(queries, k, mask)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    log(f"rank {rank}/{world}: corpus rows [{lo}, {hi}) resident, warm-up")
+    log(f"rank {rank}/{world}: corpus rows [{lo}, {hi}) resident, exchange: {cx.exchange}; warm-up")
     # clocks are sampled every 20 ms from the warm-up on (same load as the timed steps): a sharded timed region
     # can be shorter than one nvidia-smi sampling period.  Exactly W warm-up steps are run.
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(cx.local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.15)  # let nvidia-smi come up
     for _ in range(args.warmup):
         step_device()
-    barrier()
+    cx.barrier()
     log("timed region")
     launches0 = eng.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    cx.barrier()
     ev0.record()
     for _ in range(args.steps):
         step_device()
     ev1.record()
-    barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
+    cx.barrier()
+    elapsed_ms = cx.max_over_ranks(ev0.elapsed_time(ev1))
     launches = eng.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
     qps = nq * args.steps / (elapsed_ms * 1e-3)
     log(f"value {qps:.1f} q/s; end-to-end leg")
 
     # ---- end to end: the step's queries start in pinned host memory and its results end in host memory, with
-    # the copies and the synchronise inside the timed region.
+    # the copies and the synchronise inside the timed region, through the C-ABI host entry points.
     #   e2e.value        one public call per STEP: the 64 queries go up in one H2D copy, 64 single-query scans
-    #                    (N > 1: + all-gather + merge), the 64 x k pairs come back, one synchronise
+    #                    (N > 1: + the fused exchange), the 64 x k pairs come back, one synchronise
     #   e2e.per_request  one public call per QUERY, each with its own H2D, D2H and synchronise (a latency-bound
     #                    serving loop with a single request in flight)
     out_s = torch.empty(nq, k, dtype=torch.float32).pin_memory()
@@ -287,45 +396,39 @@ def run_b200(args):
     out_s1 = torch.empty(1, k, dtype=torch.float32).pin_memory()
     out_i1 = torch.empty(1, k, dtype=torch.int64).pin_memory()
     q_dev = torch.empty(nq, DIM, dtype=torch.float16, device=dev)
+    peer = world > 1 and eng.comm_world == world
+
+    def host_call(qh, os_, oi_):
+        if world == 1:
+            eng.dense_topk_host(corpus, qh, k, mask_dev=mask, metric=_ffi.RS_METRIC_COSINE, id_base=lo,
+                                out_scores=os_, out_ids=oi_)
+        elif peer:
+            eng.dense_topk_sharded_host(corpus, qh, k, mask_dev=mask, metric=_ffi.RS_METRIC_COSINE, id_base=lo,
+                                        out_scores=os_, out_ids=oi_)
+        else:  # NCCL plumbing (only when the peer exchange could not be opened)
+            n_ = qh.shape[0] if qh.dim() == 2 else 1
+            q_dev[:n_].copy_(qh.reshape(n_, DIM), non_blocking=True)
+            s, i = index.search(q_dev[:n_], k, mask)
+            os_.copy_(s, non_blocking=True)
+            oi_.copy_(i, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
 
     def step_e2e():
-        if world == 1:
-            # the C-ABI host entry point: H2D(queries) -> scans -> (score, id) pairs in host memory -> synchronise
-            eng.dense_topk_host(corpus, queries_host, k, mask_dev=mask, metric=_ffi.RS_METRIC_COSINE,
-                                id_base=lo, out_scores=out_s, out_ids=out_i)
-        else:
-            q_dev.copy_(queries_host, non_blocking=True)
-            s, i = index.search(q_dev, k, mask)
-            out_s.copy_(s, non_blocking=True)
-            out_i.copy_(i, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+        host_call(queries_host, out_s, out_i)
 
     def step_per_request():
         for j in range(nq):
-            if world == 1:
-                eng.dense_topk_host(corpus, queries_host[j], k, mask_dev=mask, metric=_ffi.RS_METRIC_COSINE,
-                                    id_base=lo, out_scores=out_s1, out_ids=out_i1)
-            else:
-                q_dev[:1].copy_(queries_host[j: j + 1], non_blocking=True)
-                s, i = index.search(q_dev[:1], k, mask)
-                out_s1.copy_(s, non_blocking=True)
-                out_i1.copy_(i, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
+            host_call(queries_host[j], out_s1, out_i1)
 
     def timed_host_loop(fn, steps):
         for _ in range(max(1, min(args.warmup, 2))):
             fn()
-        barrier()
+        cx.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
             fn()
-        barrier()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        return nq * steps / dt
+        cx.barrier()
+        return nq * steps / cx.max_over_ranks(time.perf_counter() - t0)
 
     e2e_steps = args.steps
     e2e_qps = timed_host_loop(step_e2e, e2e_steps)
@@ -335,102 +438,118 @@ def run_b200(args):
 
     # ---- sanity check of the timed configuration against an independent torch computation on the
     # GPU (not the oracle, not our kernel): fp32 matmul + mask + torch.topk over this rank's shard
-    check = None
-    if rank == 0:
-        s, i = eng.dense_topk(corpus, queries[:1], k, mask=mask, id_base=lo)
-        ref = (corpus.float() @ queries[0].float()) / queries[0].float().norm()
-        ref = torch.where(torch.from_numpy(bits).to(dev), ref, torch.full_like(ref, float("-inf")))
-        rs, ri = torch.topk(ref, k)
-        check = bool(torch.equal(ri + lo, i[0]) and torch.allclose(rs, s[0], rtol=1e-3, atol=1e-6))
+    s, i = eng.dense_topk(corpus, queries[:1], k, mask=mask, id_base=lo)
+    ref = (corpus.float() @ queries[0].float()) / queries[0].float().norm()
+    ref = torch.where(torch.from_numpy(bits).to(dev), ref, torch.full_like(ref, float("-inf")))
+    rs, ri = torch.topk(ref, k)
+    check = bool(torch.equal(ri + lo, i[0]) and torch.allclose(rs, s[0], rtol=1e-3, atol=1e-6))
     # ... and the end-to-end leg returned, in host memory, what the device-resident leg computes (every rank takes
-    # part: with N > 1 both legs contain the all-gather)
+    # part: with N > 1 both legs contain the exchange)
     step_e2e()
     s_all, i_all = step_device()
     same = bool(torch.equal(i_all.cpu(), out_i) and torch.allclose(s_all.cpu(), out_s, rtol=1e-6, atol=0))
-    if rank == 0:
-        check = check and same
+    check = cx.all_ok(check and same)
 
     # ---- roofline of the scan kernel
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
-    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
     rows_local = hi - lo
     passing = int(bits.sum())
     alg_bytes = passing * DIM * 2 + (rows_local + 7) // 8 + DIM * 2 + k * 12
     scan_launches = nq * args.steps
     avg_launch_ms = elapsed_ms / scan_launches  # launches are back to back on one stream
     achieved = alg_bytes / (avg_launch_ms * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this exact workload from the committed
-    # `ncu --set full` capture (profiles/r01_dense_scan_v4_ncu.txt): 2.048201 GB + 3.71 MB; null for other shapes
-    traffic = 2_051_912_488 if (world == 1 and args.rows == N_ROWS and k == TOPK and args.mask_p >= 1.0) else None
-    roofline = {"bound": "hbm", "kernel": "dense_scan_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this exact workload from the committed
+    # `ncu --set full` capture of the SAME kernel source (profiles/dense_scan_traffic.json names the source hash it
+    # was taken from); null when the kernel changed since, or for any other shape
+    traffic = None
+    if world == 1 and args.rows == N_ROWS and k == TOPK and args.mask_p >= 1.0:
+        traffic = committed_traffic("dense_scan.cu", "config2")
+    roofline = {"bound": "hbm", "kernel": "dense_scan_kernel", "achieved": achieved, "peak": cx.hbm_peak, "unit": "GB/s",
+                "frac": achieved / cx.hbm_peak, "traffic": traffic, "peak_source": cx.peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": avg_launch_ms * 1e3}
 
     extra = {}
-    if rank == 0 and world == 1 and not args.no_extra:
-        extra = extra_measurements(eng, corpus, queries, dev, hbm_peak, peaks)
+    if not args.no_extra:
+        if world == 1:
+            try:
+                extra.update(extra_single_gpu(cx, corpus, queries))
+            except Exception as e:  # noqa: BLE001
+                extra["single_gpu_error"] = repr(e)
+        del corpus, index, mask
+        torch.cuda.empty_cache()
+        eng.set_dense_impl(_ffi.RS_DENSE_AUTO)
+        eng.set_maxsim_impl(_ffi.RS_MAXSIM_AUTO)
+        for name, fn in (("config4_sharded", extra_config4_sharded), ("config5", extra_config5)):
+            log(f"extra: {name}")
+            try:
+                extra[name] = fn(cx)
+            except Exception as e:  # noqa: BLE001 — keep the headline line even if an extra fails on this rank
+                extra[name] = {"error": repr(e)}
+            torch.cuda.empty_cache()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        host = corpus.cpu().numpy().astype(np.float32)
+        threads = set_host_threads()
+        host = make_corpus(0, args.rows, dev).cpu().numpy().astype(np.float32)
         qh = queries_host.numpy().astype(np.float32)
+        _, bits_all = make_mask_words(0, args.rows, args.mask_p)
         probe_q = args.cpu_queries or 0
         if probe_q == 0:
-            v, dt = cpu_reference_qps(host, qh, bits, k, 2)
+            v, dt = cpu_reference_qps(host, qh, bits_all, k, 2)
             probe_q = int(min(64, max(4, 15.0 / (dt / 2))))
-        v, dt = cpu_reference_qps(host, qh, bits, k, probe_q)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        v, dt = cpu_reference_qps(host, qh, bits_all, k, probe_q)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": f"{probe_q} full-corpus queries of the same workload in {dt:.1f} s (numpy restatement "
-                                  "of qdrant-client local mode, oracle/dense.py)"}
+                                  "of qdrant-client local mode, oracle/dense.py; parity unpinned)"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f16 in / f32 accumulate", "data": "synthetic",
-            "config": {"workload": "config2", "rows": args.rows, "rows_per_gpu": rows_local, "dim": DIM, "k": k,
-                       "mask_p": args.mask_p, "queries_per_step": nq, "parallelism": f"row-shard x{world}",
-
-                       "l2": (f"inputs larger than L2: every query re-reads its {rows_local * DIM * 2 / 1e6:.0f} MB shard "
-                              "(126 MB L2, loads carry an evict_first hint)")},
+            "config": config_dict(args, world),
             "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": nq * DIM * 2, "d2h_bytes_per_step": nq * k * 12,
                     "steps": e2e_steps, "calls_per_step": 1,
                     "per_request": {"value": per_request_qps, "unit": UNIT, "calls_per_step": nq,
                                     "steps": per_request_steps}},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
-            "parity_spot_check": check, "extra": extra,
+            "parity_spot_check": check, "exchange": cx.exchange, "extra": extra,
         }
         print(json.dumps(line))
     if world > 1:
+        cx.barrier()
+        if eng.comm_world:
+            eng.comm_close()
         dist.destroy_process_group()
     return 0
 
 
-def extra_measurements(eng, corpus, queries, dev, hbm_peak, peaks):
-    """Secondary numbers (not the headline): masked scans, MaxSim config 4a on the tensor roof."""
-    import numpy as np
+def committed_traffic(source: str, workload: str):
+    """dram bytes per launch from profiles/<kernel>_traffic.json if it was captured from the current kernel source."""
+    import hashlib
+
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            rec = json.load(f)[source][workload]
+        with open(os.path.join(ROOT, "automative-rag_b200", "csrc", source), "rb") as f:
+            if hashlib.sha256(f.read()).hexdigest()[:16] != rec["source_sha16"]:
+                return None
+        return rec["dram_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        return None
+
+
+# ------------------------------------------------------------------------------------------ N = 1 extras
+def extra_single_gpu(cx, corpus, queries):
+    """Secondary single-GPU numbers: masked scans, k = 100 / 1000, config 3, config 1, config 4a on one GPU."""
     import torch
 
     from automative_rag_b200 import _ffi
 
+    eng, dev, peaks, hbm_peak = cx.eng, cx.dev, cx.peaks, cx.hbm_peak
     out = {}
 
     def timed(fn, iters, warm=3):
-        for _ in range(warm):
-            fn()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(iters):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / iters
+        return cx.timed(fn, iters, warm)
 
     n = corpus.shape[0]
     for p in (0.5, 0.1):
@@ -446,7 +565,6 @@ def extra_measurements(eng, corpus, queries, dev, hbm_peak, peaks):
 
     # BASELINE config 3: 1024 queries x 10M x 1024 bf16, top-100 — tcgen05 GEMM + fused per-query top-k
     try:
-        del corpus
         torch.cuda.empty_cache()
         n3, nq3, k3 = 10_000_000, 1024, 100
         c3 = torch.empty(n3, DIM, dtype=torch.bfloat16, device=dev)
@@ -460,11 +578,10 @@ def extra_measurements(eng, corpus, queries, dev, hbm_peak, peaks):
         eng.set_dense_impl(_ffi.RS_DENSE_TCGEN05)
         ms = timed(lambda: eng.dense_topk(c3, q3, k3), 5, warm=2)
         fl = 2.0 * nq3 * n3 * DIM
-        tf_sus = peaks.get("bf16_tflops_sustained", 1400.0)
         out["dense_batch_config3"] = {
             "ms_per_batch": ms, "queries_per_s": nq3 / ms * 1e3, "rows": n3, "queries": nq3, "k": k3,
-            "roofline": {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": tf_sus, "unit": "TFLOP/s",
-                         "frac": fl / ms / 1e9 / tf_sus, "traffic": None,
+            "roofline": {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": cx.tf_sustained, "unit": "TFLOP/s",
+                         "frac": fl / ms / 1e9 / cx.tf_sustained, "traffic": None,
                          "peak_source": "measured sustained" if "bf16_tflops_sustained" in peaks else "fallback"}}
         del c3
         torch.cuda.empty_cache()
@@ -504,57 +621,280 @@ def extra_measurements(eng, corpus, queries, dev, hbm_peak, peaks):
             rr._compute_maxsim_scores(q1d, d1d)
         dt = (_time.perf_counter() - t0) / 50
         out["maxsim_config1_fp16_device_inputs"] = {"ms_per_query_e2e": dt * 1e3, "queries_per_s": 1.0 / dt}
+        threads = set_host_threads()
         omaxsim.maxsim_scores(q1, d1)
         t0 = _time.perf_counter()
         for _ in range(20):
             omaxsim.maxsim_scores(q1, d1)
         dt = (_time.perf_counter() - t0) / 20
-        out["maxsim_config1_cpu_port"] = {"ms_per_query": dt * 1e3, "queries_per_s": 1.0 / dt,
-                                          "cores": torch.get_num_threads(), "kind": "port"}
+        out["maxsim_config1_cpu_port"] = {"ms_per_query": dt * 1e3, "queries_per_s": 1.0 / dt, "cores": threads,
+                                          "kind": "port"}
     except Exception as e:  # noqa: BLE001
         out["maxsim_config1"] = {"error": str(e)}
 
-    # MaxSim config 4a: 256 queries x 32 tokens vs 1000 shared candidates x 300 tokens, d=128, bf16
-    nq, lq, d, nd, ld = 256, 32, 128, 1000, 300
-    g = torch.Generator(device=dev).manual_seed(6)
-    q = torch.randn(nq, lq, d, generator=g, device=dev).bfloat16()
-    toks = torch.randn(nd * ld, d, generator=torch.Generator(device=dev).manual_seed(7), device=dev).bfloat16()
-    off = (torch.arange(nd + 1, dtype=torch.int32) * ld).to(dev)
-    flops = 2.0 * nq * lq * nd * ld * d
-    tf_peak = peaks.get("bf16_tflops", 1590.0)
-    for name, impl in (("tcgen05", _ffi.RS_MAXSIM_TCGEN05), ("mma_sync", _ffi.RS_MAXSIM_MMA)):
-        try:
-            eng.set_maxsim_impl(impl)
-            ms = timed(lambda: eng.maxsim(q, toks, off), 20)
-            out[f"maxsim_4a_{name}"] = {
-                "ms_per_batch": ms, "queries_per_s": nq / ms * 1e3,
-                "roofline": {"bound": "tensor", "achieved": flops / ms / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
-                             "frac": flops / ms / 1e9 / tf_peak, "traffic": None,
-                             "peak_source": "measured burst" if "bf16_tflops" in peaks else "fallback"}}
-        except Exception as e:  # noqa: BLE001
-            out[f"maxsim_4a_{name}"] = {"error": str(e)}
-        finally:
-            eng.set_maxsim_impl(_ffi.RS_MAXSIM_AUTO)
-    # BASELINE config 4b: per-query candidate lists (the retrieve-then-rerank shape): 256 queries, each with its
-    # own 1000 documents drawn from a 20000-document pool (1.5 GB of bf16 tokens, 12x the L2) -> HBM-bound:
-    # 256 * 1000 * 300 * 128 * 2 B = 19.66 GB of token reads per batch.  AUTO picks the document-streaming tcgen05
-    # kernel (maxsim_cand_tc5.cu); traffic = dram bytes of one launch from profiles/r01_maxsim_cand_v1_ncu.txt.
+    # MaxSim config 4a on the legacy mma.sync kernel, for reference next to the tcgen05 number in config4_sharded
     try:
-        pool_docs, nc = 20_000, 1000
-        ptoks = torch.randn(pool_docs * ld, d, generator=torch.Generator(device=dev).manual_seed(8), device=dev).bfloat16()
-        poff = (torch.arange(pool_docs + 1, dtype=torch.int32) * ld).to(dev)
-        cand = torch.randint(0, pool_docs, (nq, nc), generator=torch.Generator(device=dev).manual_seed(9), device=dev,
-                             dtype=torch.int32)
-        ms = timed(lambda: eng.maxsim(q, ptoks, poff, cand=cand), 5, warm=2)
-        nbytes = float(nq) * nc * ld * d * 2
-        out["maxsim_4b_per_query_candidates"] = {
-            "ms_per_batch": ms, "queries_per_s": nq / ms * 1e3,
-            "roofline": {"bound": "hbm", "achieved": nbytes / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": nbytes / ms / 1e6 / hbm_peak, "traffic": 19_725_812_248, "peak_source": "measured"},
-            "impl": {_ffi.RS_MAXSIM_MMA: "mma.sync", _ffi.RS_MAXSIM_TCGEN05_CAND: "tcgen05_cand"}.get(eng.last_maxsim_impl, "?")}
+        nq, lq, d, nd, ld = 256, 32, 128, 1000, 300
+        q = torch.randn(nq, lq, d, generator=torch.Generator(device=dev).manual_seed(6), device=dev).bfloat16()
+        toks = torch.randn(nd * ld, d, generator=torch.Generator(device=dev).manual_seed(7), device=dev).bfloat16()
+        off = (torch.arange(nd + 1, dtype=torch.int32) * ld).to(dev)
+        eng.set_maxsim_impl(_ffi.RS_MAXSIM_MMA)
+        ms = timed(lambda: eng.maxsim(q, toks, off), 5)
+        fl = 2.0 * nq * lq * nd * ld * d
+        out["maxsim_4a_mma_sync"] = {"ms_per_batch": ms, "queries_per_s": nq / ms * 1e3, "tflops": fl / ms / 1e9,
+                                     "frac_of_burst": fl / ms / 1e9 / cx.tf_burst}
     except Exception as e:  # noqa: BLE001
-        out["maxsim_4b_per_query_candidates"] = {"error": str(e)}
+        out["maxsim_4a_mma_sync"] = {"error": str(e)}
+    finally:
+        eng.set_maxsim_impl(_ffi.RS_MAXSIM_AUTO)
     return out
+
+
+# ------------------------------------------------------------------------------------------ every N: config 4 sharded
+def extra_config4_sharded(cx):
+    """BASELINE config 4 with the candidates sharded by rank (SURVEY §8d row "4 sharded"): 256 queries x 32 tokens,
+    d = 128, bf16.
+      4a  1000 SHARED candidates x 300 tokens, rank r scores documents shard_bounds(1000, G, r) for every query,
+          one exchange of the [256, 1000/G] blocks.  Tensor-bound: 0.629 TFLOP per batch over G GPUs.
+      4b  every query has its OWN 1000 candidates out of a 20000-document pool whose token embeddings are owned
+          round-robin (doc % G); a rank scores the candidates it owns, one max-exchange of the [256, 1000] blocks.
+          HBM-bound: 19.66 GB of token reads per batch over G GPUs.
+    Every rank checks its sharded result bit for bit against the unsharded computation on its own GPU; rank 0 also
+    checks a sample against the CPU oracle."""
+    import numpy as np
+    import torch
+
+    from automative_rag_b200 import _ffi
+    from automative_rag_b200.distributed import ShardedCandidateMaxSim, ShardedMaxSim, shard_bounds
+    from oracle import maxsim as omaxsim
+
+    eng, dev, world, rank = cx.eng, cx.dev, cx.world, cx.rank
+    nq, lq, d, nd, ld, pool, nc = 256, 32, 128, 1000, 300, 20_000, 1000
+    out = {}
+    q = torch.randn(nq, lq, d, generator=torch.Generator(device=dev).manual_seed(6), device=dev).bfloat16()
+    toks = torch.randn(nd * ld, d, generator=torch.Generator(device=dev).manual_seed(7), device=dev).bfloat16()
+    offs = (torch.arange(nd + 1, dtype=torch.int32) * ld).to(dev)
+    lo, hi = shard_bounds(nd, world, rank)
+    loc_toks = toks[lo * ld: hi * ld].contiguous()
+    loc_off = (torch.arange(hi - lo + 1, dtype=torch.int32) * ld).to(dev)
+    sharded = ShardedMaxSim(loc_toks, loc_off, nd, engine=eng)
+    ms_a = cx.timed(lambda: sharded.scores(q), 20)
+    impl_a = eng.last_maxsim_impl
+    got = sharded.scores(q)
+    full = eng.maxsim(q, toks, offs)
+    same_a = bool(torch.equal(got, full))
+    sel = [0, 131]
+    want = omaxsim.maxsim_scores_packed(q[sel].cpu(), None, toks.cpu(), offs.cpu().numpy())
+    err_a = float(np.abs(got[sel].cpu().numpy() - want).max() / np.abs(want).max())
+    fl = 2.0 * nq * lq * nd * ld * d
+    out["maxsim_4a"] = {
+        "ms_per_batch": ms_a, "queries_per_s": nq / ms_a * 1e3, "candidates_per_gpu": hi - lo,
+        "kernel": {_ffi.RS_MAXSIM_TCGEN05: "maxsim_tc5_kernel (tcgen05, CTA pairs)", _ffi.RS_MAXSIM_TCGEN05_CAND: "maxsim_cand_tc5_kernel",
+                   _ffi.RS_MAXSIM_MMA: "maxsim_mma_kernel"}.get(impl_a, str(impl_a)),
+        "roofline": {"bound": "tensor", "achieved": fl / ms_a / 1e9 / world, "peak": cx.tf_burst, "unit": "TFLOP/s per GPU",
+                     "frac": fl / ms_a / 1e9 / world / cx.tf_burst, "traffic": None,
+                     "peak_source": "measured burst" if "bf16_tflops" in cx.peaks else "fallback",
+                     "note": "includes the exchange and the torch glue of the sharded step at N > 1"},
+        "parity": {"sharded_equals_unsharded_bitwise": cx.all_ok(same_a), "max_rel_err_vs_cpu_oracle_2_queries": err_a,
+                   "ok": cx.all_ok(same_a and err_a < 1e-3)}}
+    del toks, loc_toks, full, got
+
+    ptoks = torch.randn(pool * ld, d, generator=torch.Generator(device=dev).manual_seed(8), device=dev).bfloat16()
+    poff = (torch.arange(pool + 1, dtype=torch.int32) * ld).to(dev)
+    cand = torch.randint(0, pool, (nq, nc), generator=torch.Generator(device=dev).manual_seed(9), device=dev, dtype=torch.int32)
+    if world > 1:
+        own = torch.arange(rank, pool, world, device=dev)
+        loc_pool = ptoks.view(pool, ld * d)[own].reshape(-1, d).contiguous()
+        loc_poff = (torch.arange(own.numel() + 1, dtype=torch.int32) * ld).to(dev)
+    else:
+        loc_pool, loc_poff = ptoks, poff
+    cs = ShardedCandidateMaxSim(loc_pool, loc_poff, engine=eng)
+    ms_b = cx.timed(lambda: cs.scores(q, cand), 8, warm=2)
+    impl_b = eng.last_maxsim_impl
+    got_b = cs.scores(q, cand)
+    full_b = eng.maxsim(q, ptoks, poff, cand=cand)
+    same_b = bool(torch.equal(got_b, full_b))
+    cs_cpu = cand[sel].cpu()
+    uniq, inv = torch.unique(cs_cpu.reshape(-1).long(), return_inverse=True)
+    sub = ptoks.view(pool, ld, d)[uniq.to(dev)].reshape(-1, d).cpu()
+    sub_off = np.arange(len(uniq) + 1, dtype=np.int64) * ld
+    want_b = omaxsim.maxsim_scores_packed(q[sel].cpu(), None, sub, sub_off, cand=inv.reshape(len(sel), nc).numpy())
+    err_b = float(np.abs(got_b[sel].cpu().numpy() - want_b).max() / np.abs(want_b).max())
+    nbytes = float(nq) * nc * ld * d * 2
+    out["maxsim_4b"] = {
+        "ms_per_batch": ms_b, "queries_per_s": nq / ms_b * 1e3,
+        "kernel": {_ffi.RS_MAXSIM_TCGEN05_CAND: "maxsim_cand_tc5_kernel (tcgen05, document-streaming)",
+                   _ffi.RS_MAXSIM_MMA: "maxsim_mma_kernel"}.get(impl_b, str(impl_b)),
+        "roofline": {"bound": "hbm", "achieved": nbytes / ms_b / 1e6 / world, "peak": cx.hbm_peak, "unit": "GB/s per GPU",
+                     "frac": nbytes / ms_b / 1e6 / world / cx.hbm_peak, "traffic": None, "peak_source": cx.peak_src,
+                     "note": "owner lookup of the candidate lists and the exchange are inside the timed step"},
+        "parity": {"sharded_equals_unsharded_bitwise": cx.all_ok(same_b), "max_rel_err_vs_cpu_oracle_2_queries": err_b,
+                   "ok": cx.all_ok(same_b and err_b < 1e-3)}}
+    return out
+
+
+# ------------------------------------------------------------------------------------------ every N: config 5
+def cpu_scores(rows_f16, queries_f32_unit):
+    """fp32 CPU scores [n, nq] of fp16-rounded rows (torch CPU tensor or numpy) against unit queries, chunked."""
+    import numpy as np
+
+    rows = rows_f16.numpy() if hasattr(rows_f16, "numpy") else rows_f16
+    out = np.empty((rows.shape[0], queries_f32_unit.shape[0]), dtype=np.float32)
+    for a in range(0, rows.shape[0], 131072):
+        out[a: a + 131072] = rows[a: a + 131072].astype(np.float32) @ queries_f32_unit.T
+    return out
+
+
+def extra_config5(cx):
+    """BASELINE config 5, weak-scaled: 12.5M x 1024 fp16 rows PER GPU (seed 100 + rank), so 100M rows = 204.8 GB at
+    8 GPUs; one query at a time: exact cosine top-1000 per shard (single-query scan) -> ONE exchange (push + merge) ->
+    ColBERT MaxSim of the query's 32 tokens against the 1000 winners' token embeddings (synthetic pool of 125k
+    documents x 300 tokens x 128 bf16 per GPU, doc id -> slot id % P, owner slot % G — a benchmark-design stand-in
+    for the per-query BERT re-encoding of the reference, rerankers.py:371, which is out of scope) -> ONE max-exchange
+    -> stable top-10 (rs_rerank_postprocess).  Then the same scan strong-scaled: 12.5M rows TOTAL over the G GPUs.
+
+    Parity block, run here for `parity_queries` queries on every rank, all on host cores with numpy /
+    torch-CPU: (i) the returned stage-1 scores recomputed from the fp16 rows; (ii) threshold check: no row out of
+    >= 1M sampled non-returned rows per shard beats the k-th returned score beyond tolerance; (iii) the engine's
+    top-1000 over a 1M-row slice of every shard against the full CPU oracle of that slice (tie-aware, tests/_parity);
+    (iv) oracle MaxSim of the winners each rank owns + the oracle's stable top-10 against the returned top-10."""
+    import numpy as np
+    import torch
+
+    from automative_rag_b200 import _ffi
+    from automative_rag_b200.distributed import ShardedCandidateMaxSim, ShardedDenseIndex
+    from oracle import maxsim as omaxsim
+    from tests._parity import assert_scores_close, assert_topk_matches
+
+    args, eng, dev, world, rank = cx.args, cx.eng, cx.dev, cx.world, cx.rank
+    D, DT, LQ, LD, k1, k2 = DIM, 128, 32, 300, 1000, 10
+    n_local, p_local, nqs = args.c5_rows_per_gpu, args.c5_pool_docs_per_gpu, args.c5_queries
+    P = p_local * world
+    lo = rank * n_local
+    eng.set_dense_impl(_ffi.RS_DENSE_SCAN)
+    corpus = torch.empty(n_local, D, dtype=torch.float16, device=dev)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    for a in range(0, n_local, 500_000):
+        m = min(500_000, n_local - a)
+        blk = torch.randn(m, D, generator=g, device=dev)
+        corpus[a:a + m] = (blk / blk.norm(dim=1, keepdim=True)).half()
+    del blk
+    pool = torch.empty(p_local * LD, DT, dtype=torch.bfloat16, device=dev)  # slots rank, rank + G, ...
+    g = torch.Generator(device=dev).manual_seed(200 + rank)
+    for a in range(0, p_local * LD, 4_000_000):
+        m = min(4_000_000, p_local * LD - a)
+        pool[a:a + m] = torch.randn(m, DT, generator=g, device=dev).bfloat16()
+    pool_off = (torch.arange(p_local + 1, dtype=torch.int64) * LD).to(torch.int32).to(dev)
+    gq = torch.Generator().manual_seed(2)
+    queries = torch.randn(nqs, D, generator=gq)
+    queries = (queries / queries.norm(dim=1, keepdim=True)).half()
+    qtok_h = torch.randn(nqs, LQ, DT, generator=gq).bfloat16()
+    queries_d, qtok = queries.to(dev), qtok_h.to(dev)
+    index = ShardedDenseIndex(corpus, lo, engine=eng, metric=_ffi.RS_METRIC_COSINE)
+    rerank = ShardedCandidateMaxSim(pool, pool_off, engine=eng)
+
+    def one_query(j):
+        s1, ids = index.search(queries_d[j:j + 1], k1)                      # [1, k1] global ids, same on every rank
+        slot = torch.where(ids >= 0, ids % P, torch.full_like(ids, -1)).to(torch.int32)
+        sc = rerank.scores(qtok[j:j + 1], slot)                              # [1, k1], owners' scores exchanged
+        top_idx, top_sc = eng.rerank_postprocess(sc, None, k2)               # stable order, [:k2]
+        return ids[0][top_idx[0].long()], top_sc[0], ids[0], s1[0], sc[0]
+
+    # stage breakdown (device time, max over ranks)
+    ms_total = cx.timed(lambda: [one_query(j) for j in range(nqs)], 1, warm=1) / nqs
+    ms_scan = cx.timed(lambda: [eng.dense_topk(corpus, queries_d[j:j + 1], k1, id_base=lo) for j in range(nqs)], 1, warm=0) / nqs
+    scan_bytes = n_local * D * 2 + D * 2 + k1 * 12
+    res = {
+        "workload": "config5 (weak scaling)", "rows_per_gpu": n_local, "rows_total": n_local * world, "corpus_gb_total": n_local * world * D * 2 / 1e9,
+        "pool_docs": P, "k1": k1, "k2": k2, "queries": nqs, "ms_per_query": ms_total, "queries_per_s": 1e3 / ms_total,
+        "row_scans_per_s": n_local * world * 1e3 / ms_total, "stage1_scan_ms": ms_scan,
+        "exchange_and_rerank_ms": ms_total - ms_scan, "exchange": cx.exchange,
+        "roofline": {"bound": "hbm", "kernel": "dense_scan_kernel (k = 1000)", "achieved": scan_bytes / ms_total / 1e6,
+                     "peak": cx.hbm_peak, "unit": "GB/s per GPU", "frac": scan_bytes / ms_total / 1e6 / cx.hbm_peak, "traffic": None,
+                     "peak_source": cx.peak_src,
+                     "note": "whole query (scan + exchange + MaxSim + exchange + top-10) against the bytes of the scan alone"},
+    }
+
+    # ---- parity block
+    if not args.no_parity:
+        t0 = time.perf_counter()
+        npq = min(2, nqs)
+        ok, detail = True, {}
+        try:
+            qf = queries[:npq].float().numpy()
+            qf = qf / np.linalg.norm(qf, axis=1, keepdims=True)
+            outs = [one_query(j) for j in range(npq)]
+            torch.cuda.synchronize()
+            # (i) returned stage-1 scores of the ids this rank owns, recomputed on the CPU
+            worst_i = 0.0
+            for j in range(npq):
+                ids, s1 = outs[j][2].cpu(), outs[j][3].cpu().numpy()
+                mine = (ids >= lo) & (ids < lo + n_local)
+                rows = corpus[(ids[mine] - lo).to(dev)].cpu()
+                want = cpu_scores(rows, qf[j:j + 1])[:, 0]
+                assert_scores_close(s1[mine.numpy()], want, what="config5 (i) returned scores")
+                if len(want):
+                    worst_i = max(worst_i, float(np.abs(s1[mine.numpy()] - want).max()))
+            detail["i_returned_scores_max_abs_err"] = cx.max_over_ranks(worst_i)
+            # (ii) threshold check on >= 1M sampled non-returned rows of this shard (1024 random blocks of 1024 rows)
+            nblk, blk_rows = 1024, 1024
+            rng = np.random.default_rng(1234 + rank)
+            starts = np.sort(rng.choice(max(1, (n_local - blk_rows) // blk_rows), size=min(nblk, max(1, n_local // blk_rows)), replace=False)) * blk_rows
+            idx = (torch.from_numpy(starts).to(dev)[:, None] + torch.arange(blk_rows, device=dev)[None, :]).reshape(-1)
+            sample = corpus[idx].cpu()
+            sc_cpu = cpu_scores(sample, qf)
+            beat = 0
+            for j in range(npq):
+                ids, s1 = outs[j][2].cpu().numpy(), outs[j][3].cpu().numpy()
+                kth = float(s1[ids >= 0].min())
+                returned = np.isin(idx.cpu().numpy() + lo, ids)
+                rest = sc_cpu[~returned, j]
+                tol = 1e-3 * max(abs(kth), float(np.abs(rest).max())) + 1e-6
+                beat += int((rest > kth + tol).sum())
+            detail["ii_threshold_sampled_rows_per_shard"] = int(idx.numel())
+            detail["ii_rows_beating_kth"] = int(cx.max_over_ranks(float(beat)))
+            ok &= beat == 0
+            # (iii) the engine's top-k1 over a 1M-row slice of this shard against the full CPU oracle of the slice
+            n_slice = min(1_000_000, n_local)
+            sl = corpus[:n_slice]
+            s_sl, i_sl = eng.dense_topk(sl, queries_d[:npq], k1, id_base=lo)
+            all_sc = cpu_scores(sl.cpu(), qf)
+            for j in range(npq):
+                assert_topk_matches(s_sl[j].cpu().numpy(), i_sl[j].cpu().numpy(), all_sc[:, j], np.ones(n_slice, bool), k1, id_base=lo)
+            detail["iii_oracle_slice_rows"] = n_slice
+            # (iv) oracle MaxSim of the winners this rank owns, then the oracle's stable top-k2 over the merged scores
+            worst_iv = 0.0
+            for j in range(npq):
+                top_ids, top_sc, ids, _, sc = [t.cpu() for t in outs[j]]
+                slot = ids % P
+                mine = (ids >= 0) & (slot % world == rank)
+                li = (slot[mine] // world).to(dev)
+                docs = pool.view(p_local, LD, DT)[li].cpu()
+                want = omaxsim.maxsim_scores(qtok_h[j], [docs[t] for t in range(docs.shape[0])])
+                assert_scores_close(sc[mine].numpy(), want, atol=1e-3, what="config5 (iv) MaxSim of owned winners")
+                if len(want):
+                    worst_iv = max(worst_iv, float(np.abs(sc[mine].numpy() - want).max() / np.abs(want).max()))
+                order = omaxsim.hybrid_rerank(sc.numpy(), None, top_k=k2)  # stable sort of the merged scores
+                ok &= [int(ids[i]) for i, _ in order] == top_ids.tolist()
+                ok &= bool(np.allclose([v for _, v in order], top_sc.numpy(), rtol=0, atol=0))
+            detail["iv_maxsim_max_rel_err"] = cx.max_over_ranks(worst_iv)
+        except AssertionError as e:
+            ok = False
+            detail["failure"] = str(e)[:300]
+        res["parity"] = cx.all_ok(ok)
+        res["parity_detail"] = {**detail, "queries_checked": npq, "seconds": round(time.perf_counter() - t0, 1),
+                                "protocol": "SURVEY §8d (i)-(iii) + oracle MaxSim/rerank of the winners; CPU numpy / torch-CPU"}
+
+    # ---- the same scan strong-scaled: 12.5M rows in total, every rank scans the first 12.5M / G rows of its shard
+    n_strong = n_local // world
+    strong = ShardedDenseIndex(corpus[:n_strong], rank * n_strong, engine=eng, metric=_ffi.RS_METRIC_COSINE)
+    ms_strong = cx.timed(lambda: [strong.search(queries_d[j:j + 1], TOPK) for j in range(nqs)], 2, warm=1) / nqs
+    sb = n_strong * D * 2
+    res["strong_12p5m"] = {"rows_total": n_strong * world, "rows_per_gpu": n_strong, "k": TOPK, "ms_per_query": ms_strong,
+                           "queries_per_s": 1e3 / ms_strong,
+                           "roofline": {"bound": "hbm", "achieved": sb / ms_strong / 1e6, "peak": cx.hbm_peak, "unit": "GB/s per GPU",
+                                        "frac": sb / ms_strong / 1e6 / cx.hbm_peak, "traffic": None, "peak_source": cx.peak_src}}
+    return res
 
 
 def main():

@@ -34,6 +34,10 @@
  *   rs_topk_merge
  *       has no reference counterpart (the reference is single-GPU); it merges
  *       per-shard top-k lists after the one all-gather of SURVEY.md §8e.
+ *   rs_comm_*, rs_allgather_topk, rs_allgather, rs_allreduce_max_f32,
+ *   rs_dense_topk_sharded_host
+ *       the one exchange step per sharded stage (SURVEY.md §8b "rs_allgather_topk(comm, ...)",
+ *       §8e) as the engine's own kernels over NVLink peer memory; no reference counterpart.
  *
  * Result order everywhere: score descending, ties by ascending id — a valid
  * refinement of the reference's stable `sorted(..., reverse=True)` for rerank
@@ -67,7 +71,8 @@ enum {
   RS_ERR_UNSUPPORTED = -2,   /* shape / dtype outside what the kernels implement          */
   RS_ERR_CUDA = -3,          /* a CUDA runtime / driver call failed                       */
   RS_ERR_NO_DEVICE = -4,     /* no sm_100 device visible: there is NO CPU fallback        */
-  RS_ERR_NOMEM = -5
+  RS_ERR_NOMEM = -5,
+  RS_ERR_COMM = -6           /* a peer's wire block could not be mapped (CUDA IPC / peer access)  */
 };
 
 /* element types of embedding buffers */
@@ -173,11 +178,15 @@ int rs_topk_merge(rs_handle* h, const float* scores, const int64_t* ids, int32_t
  *                (rerankers.py:255-261): lq > 2 -> drop token 0 and token lq-1, else all ones
  *   doc_tokens   [n_tokens, d] dtype, packed;  doc i = rows doc_offsets[i] .. doc_offsets[i+1]
  *   n_tokens     rows in doc_tokens (>= doc_offsets[nd]); bounds the TMA tensor map
- *   doc_offsets  [nd + 1] int32 (device), non-decreasing, every doc non-empty
+ *   doc_offsets  [nd + 1] int32 (device), non-decreasing; an empty document scores -inf
  *   cand         NULL: every query scores all nd docs (the reference's batch_rerank_queries
- *                shape, rerankers.py:583-593); else [nq, nc] int32 doc indices per query
+ *                shape, rerankers.py:583-593); else [nq, nc] int32 doc indices per query; an
+ *                index outside [0, nd) is an empty document (score -inf) on every kernel
  *   out_scores   [nq, nd] (cand == NULL) or [nq, nc] fp32, in input order
- *   out_argmax   NULL, or int32 [nq, nd|nc, lq]: index within the doc of the max token
+ *   out_argmax   NULL, or int32 [nq, nd|nc, lq]: index within the doc of the max token (the first
+ *                one on ties) — _explain_colbert_matches, rerankers.py:489-492
+ *   out_tokmax   NULL, or fp32 [nq, nd|nc, lq]: max_j <Q[q,i,:], D[doc,j,:]> itself, the
+ *                "similarity" the explanations report per query token (rerankers.py:493-501)
  *
  *   score(q, doc) = sum_i w[q,i] * max_j <Q[q,i,:], D[doc,j,:]>,  fp32 accumulation.
  *   dtype RS_F32 runs an exact-fp32 CUDA-core kernel (small shapes, deployed sizes).
@@ -185,7 +194,7 @@ int rs_topk_merge(rs_handle* h, const float* scores, const int64_t* ids, int32_t
 int rs_maxsim(rs_handle* h, const void* q, int32_t nq, int32_t lq, int32_t d, int32_t dtype,
               const float* q_weight, const void* doc_tokens, int64_t n_tokens,
               const int32_t* doc_offsets, int32_t nd, const int32_t* cand, int32_t nc,
-              float* out_scores, int32_t* out_argmax, void* stream);
+              float* out_scores, int32_t* out_argmax, float* out_tokmax, void* stream);
 
 /*
  * Rerank tail (rerankers.py:302-343): per query row of `scores` [nq, n]:
@@ -214,6 +223,58 @@ int rs_rerank_postprocess(rs_handle* h, const float* scores, const float* other,
 int rs_filter_mask(rs_handle* h, const int32_t* const* cols, int32_t nclauses,
                    const int32_t* values, const int32_t* val_offsets, const uint32_t* tombstone,
                    int64_t n, uint32_t* out_mask, void* stream);
+
+/*
+ * ---- Multi-GPU exchange over NVLink / NVSwitch peer memory -------------------
+ *
+ * One process (or thread) per GPU, one handle per GPU.  Setup, once:
+ *   1. every rank calls rs_comm_export: allocates this rank's WIRE BLOCK (2 x world slots of
+ *      `slot_bytes`, plus flags) and fills a 128-byte handle describing it;
+ *   2. the ranks exchange the handles by any host-side means (torch.distributed, MPI, a file ...);
+ *   3. every rank calls rs_comm_open with all `world` handles in rank order: peers' blocks are
+ *      mapped with CUDA IPC (ranks in other processes) or direct peer access (same process).
+ * After that a collective is ONE kernel per rank: push the local contribution into every peer's
+ * wire block over NVLink, raise a flag, wait for the peers' flags, consume out of local memory —
+ * no NCCL, no host round trip.  Every rank must call the same collectives in the same order;
+ * calls are stream-ordered like every other entry point.  A peer that never arrives makes the
+ * kernel trap after 2 s (RS_ERR_CUDA on the next call) instead of hanging the device.
+ * slot_bytes bounds one rank's contribution per call: nq * k_in * 12 bytes for rs_allgather_topk.
+ */
+#define RS_COMM_HANDLE_BYTES 128
+#define RS_COMM_MAX_WORLD 8
+
+int rs_comm_export(rs_handle* h, int32_t world, int32_t rank, int64_t slot_bytes, void* out_handle /* [128] */);
+int rs_comm_open(rs_handle* h, const void* handles /* [world][RS_COMM_HANDLE_BYTES], rank order */);
+int rs_comm_close(rs_handle* h); /* unmaps the peers and frees the wire block; barrier across ranks first */
+/* world == 0 when no exchange is open */
+int rs_comm_info(const rs_handle* h, int32_t* world, int32_t* rank, int64_t* slot_bytes);
+
+/*
+ * The exchange of the dense stage: every rank contributes its LOCAL top-k lists
+ * (local_scores / local_ids [nq, k_in], what rs_dense_topk wrote for its shard, ids already global
+ * through id_base) and receives the merged global top-k_out of every query — gather and k-way
+ * merge fused in one kernel.  Output order (score desc, id asc), identical on every rank and
+ * bit-identical to rs_topk_merge over the gathered lists.  world * k_in <= 16384.
+ */
+int rs_allgather_topk(rs_handle* h, const float* local_scores, const int64_t* local_ids, int32_t nq,
+                      int32_t k_in, int32_t k_out, float* out_scores, int64_t* out_ids, void* stream);
+
+/* Plain all-gather: out [world][bytes] <- every rank's `local` (bytes % 16 == 0, 16-byte aligned). */
+int rs_allgather(rs_handle* h, const void* local, int64_t bytes, void* out, void* stream);
+
+/* Element-wise max over ranks of fp32 vectors — the exchange of the MaxSim stage when every
+ * candidate is scored by the one rank that owns its token embeddings and all others contribute
+ * -inf: out[i] = max over ranks of local[i]. */
+int rs_allreduce_max_f32(rs_handle* h, const float* local, int64_t n, float* out, void* stream);
+
+/* rs_dense_topk_host against a row-sharded corpus: host queries in, merged global (score, id)
+ * pairs out in host memory on every rank; H2D, local scan, the fused exchange above and the
+ * synchronise all on `stream`.  mask_dev covers this rank's rows. */
+int rs_dense_topk_sharded_host(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_t dtype,
+                               const float* inv_norm, int32_t metric, const void* queries_host,
+                               int32_t nq, const uint32_t* mask_dev, int64_t mask_stride_words,
+                               int32_t k, int64_t id_base, float* out_scores_host,
+                               int64_t* out_ids_host, void* stream);
 
 #ifdef __cplusplus
 }

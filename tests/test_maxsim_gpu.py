@@ -66,7 +66,7 @@ def _batch_case(seed, nq, lq, d, lens, dtype):
     (9, 32, 128, [1, 2, 31, 32, 33, 255, 256, 257, 511, 513, 700]),  # ragged incl. 1-token docs
     (64, 32, 64, [180] * 40),                                  # d = 64, many query tiles -> several CTAs per range
     (5, 20, 128, [64, 100, 300, 17]),                          # lq < 32 -> zero-padded query rows (TMA OOB fill)
-    (6, 45, 128, [90] * 12),                                   # lq in (32, 64] -> two warps per query, atomics
+    (6, 45, 128, [90] * 12),                                   # lq in (32, 64] -> two warps per query, fixed-order sum
     (3, 100, 64, [50, 60, 70]),                                # lq in (64, 128]
     (16, 32, 128, [300] * 300),                                # more docs than SMs / groups
 ])
@@ -96,8 +96,72 @@ def test_auto_dispatch_picks_tcgen05_for_shared_candidates(engine):
     assert engine.last_maxsim_impl == _ffi.RS_MAXSIM_TCGEN05
     engine.maxsim(q[:1].to(engine.device), toks, off)  # a single query: the document-streaming tcgen05 kernel
     assert engine.last_maxsim_impl == _ffi.RS_MAXSIM_TCGEN05_CAND
-    engine.maxsim(q[:1].to(engine.device), toks, off, want_argmax=True)  # argmax: general mma.sync kernel
+    engine.maxsim(q[:1].to(engine.device), toks, off, want_argmax=True)  # argmax: epilogue of the same tcgen05 kernel
+    assert engine.last_maxsim_impl == _ffi.RS_MAXSIM_TCGEN05_CAND
+    q7, docs7 = _batch_case(2, 2, 32, 768, [256] * 5, torch.float16)  # the deployed hidden size (rerankers.py:118-120)
+    toks7, off7 = pack_documents(docs7, engine.device, torch.float16)
+    engine.maxsim(q7.to(engine.device), toks7, off7)
+    assert engine.last_maxsim_impl == _ffi.RS_MAXSIM_TCGEN05_CAND
+    q9, docs9 = _batch_case(3, 2, 32, 80, [40] * 3, torch.float16)   # d % 64 != 0: the general mma.sync kernel
+    toks9, off9 = pack_documents(docs9, engine.device, torch.float16)
+    engine.maxsim(q9.to(engine.device), toks9, off9)
     assert engine.last_maxsim_impl == _ffi.RS_MAXSIM_MMA
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("name", sorted(MAXSIM_CASES))
+def test_tcgen05_candidate_kernel_argmax_and_token_maxima(engine, name, dtype):
+    """the explanations path (arg-max document token and the maximum itself per query token,
+    rerankers.py:489-501) and the deployed d = 768 run on the tcgen05 candidate kernel, checked against the oracle
+    on the reference's golden cases (incl. `deployed768`: 32 x 768 query vs 256-token documents)."""
+    q, docs = make_maxsim_case(MAXSIM_CASES[name])
+    if q.shape[-1] % 64:
+        pytest.skip("d not a multiple of 64: mma.sync path")
+    scale = 0.125 if dtype == torch.float16 else 1.0
+    q16 = (q * scale).to(dtype)
+    d16 = [(d * scale).to(dtype) for d in docs]
+    toks, off = pack_documents(d16, engine.device, dtype)
+    got, arg, tmax = engine.maxsim(q16.to(engine.device), toks, off, want_argmax=True, want_tokmax=True)
+    assert engine.last_maxsim_impl == _ffi.RS_MAXSIM_TCGEN05_CAND
+    want, want_arg = omaxsim.maxsim_scores(q16, d16, return_argmax=True)
+    assert_scores_close(got[0].cpu().numpy(), want, rtol=RTOL_16BIT, atol=1e-4, what=name)
+    ga, gm = arg[0].cpu().numpy(), tmax[0].cpu().numpy()
+    qf = q16[0].float() if q16.dim() == 3 else q16.float()
+    for j, d in enumerate(d16):
+        sim = (qf @ d.float().T).numpy()
+        rows = np.arange(sim.shape[0])
+        assert ((ga[j] >= 0) & (ga[j] < d.shape[0])).all()
+        # the arg-max token scores the row maximum (ties within tolerance may pick another token) ...
+        np.testing.assert_allclose(sim[rows, ga[j]], sim[rows, want_arg[j]], rtol=RTOL_16BIT, atol=1e-4)
+        # ... and out_tokmax is that maximum
+        np.testing.assert_allclose(gm[j], sim.max(axis=1), rtol=RTOL_16BIT, atol=1e-4)
+    # scores without the extra outputs are bit-identical (same kernel, same order of operations)
+    plain = engine.maxsim(q16.to(engine.device), toks, off)
+    if engine.last_maxsim_impl == _ffi.RS_MAXSIM_TCGEN05_CAND:
+        assert torch.equal(plain, got)
+
+
+@pytest.mark.parametrize("nq,lq,d,lens,nc", [
+    (3, 32, 768, [256] * 12, 5),       # deployed shape with candidate lists
+    (2, 32, 384, [1, 33, 129, 300], 0),  # six K blocks, one per ring stage
+    (5, 64, 256, [90, 200, 31], 2),     # two warps per query, four K blocks
+    (2, 32, 1024, [140, 260], 0),       # the widest supported row
+])
+def test_candidate_tcgen05_k_pipeline_matches_oracle(engine, nq, lq, d, lens, nc):
+    """Rows wider than one shared-memory stage: the chunk is streamed K block by K block (d / 64 blocks)."""
+    dtype = torch.bfloat16
+    q, docs = _batch_case(nq * 7 + d, nq, lq, d, lens, dtype)
+    q, docs = q * 0.25, [x * 0.25 for x in docs]
+    toks, off = pack_documents(docs, engine.device, dtype)
+    rng = np.random.default_rng(d)
+    cand = np.stack([rng.permutation(len(docs))[:nc] for _ in range(nq)]).astype(np.int32) if nc else None
+    engine.set_maxsim_impl(_ffi.RS_MAXSIM_TCGEN05_CAND)
+    try:
+        got = engine.maxsim(q.to(engine.device), toks, off, cand=None if cand is None else torch.from_numpy(cand).to(engine.device))
+    finally:
+        engine.set_maxsim_impl(_ffi.RS_MAXSIM_AUTO)
+    want = omaxsim.maxsim_scores_packed(q, None, torch.cat(docs), off.cpu().numpy(), cand)
+    assert_scores_close(got.cpu().numpy(), want, rtol=RTOL_16BIT, atol=1e-3, what=f"d = {d}")
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16])
