@@ -35,6 +35,8 @@ SIGNATURES = {
     "rs_set_maxsim_impl": (C.c_int, [_P, C.c_int]),
     "rs_set_scan_trace": (C.c_int, [_P, _P]),
     "rs_scan_plan": (C.c_int, [_I32, _I32, C.POINTER(_I64)]),
+    "rs_set_profiling": (C.c_int, [_P, C.c_int]),
+    "rs_last_call_stats": (C.c_int, [_P, _P]),
     "rs_last_dense_impl": (C.c_int, [_P]),
     "rs_last_maxsim_impl": (C.c_int, [_P]),
     "rs_dense_topk": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _I32, _P, _I64, _I32, _I64, _P, _P, _P]),
@@ -52,6 +54,15 @@ SIGNATURES = {
     "rs_allreduce_max_f32": (C.c_int, [_P, _P, _I64, _P, _P]),
     "rs_dense_topk_sharded_host": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _I32, _P, _I64, _I32, _I64, _P, _P, _P]),
 }
+
+RS_CALL_NONE, RS_CALL_DENSE_TOPK, RS_CALL_MAXSIM, RS_CALL_TOPK_MERGE, RS_CALL_ALLGATHER_TOPK = 0, 1, 2, 3, 4
+
+
+class CallStats(C.Structure):
+    """rs_call_stats of include/rag_b200.h."""
+    _fields_ = [("entry", _I32), ("kernel_family", _I32), ("launches", _I32), ("queries", _I32),
+                ("bytes_scanned", _I64), ("flops", C.c_double), ("device_ms", _F), ("merge_ms", _F)]
+
 
 _lib = None
 
@@ -156,6 +167,21 @@ class Engine:
     def set_scan_trace(self, trace: Optional[torch.Tensor]) -> None:
         """Diagnostics: int64 device tensor [8, num_sms, 8] receiving per-CTA phase time stamps (None detaches)."""
         self._check(self._lib.rs_set_scan_trace(self._h, trace.data_ptr() if trace is not None else None), "rs_set_scan_trace")
+
+    def set_profiling(self, on: bool) -> None:
+        """Per-call statistics on/off (two CUDA event records per scoring call, no synchronisation)."""
+        self._check(self._lib.rs_set_profiling(self._h, 1 if on else 0), "rs_set_profiling")
+
+    def last_call_stats(self) -> dict:
+        """Statistics of the most recent profiled call (waits for it): the engine-side counterpart of the reference's
+        `search_time_ms` / `docs_per_second` debug fields (src/services/system_service.py:336-372)."""
+        st = CallStats()
+        self._check(self._lib.rs_last_call_stats(self._h, C.byref(st)), "rs_last_call_stats")
+        d = {name: getattr(st, name) for name, _ in CallStats._fields_}
+        if st.device_ms > 0:
+            d["gb_per_s"] = st.bytes_scanned / st.device_ms / 1e6
+            d["tflop_per_s"] = st.flops / st.device_ms / 1e9
+        return d
 
     @property
     def last_dense_impl(self) -> int:

@@ -56,7 +56,8 @@ constexpr uint32_t kDtStageBytes = kDtMT * kDtABytes + kDtBBytes;
 struct DenseTcParams {
   const void* queries;      // [nq, d] (for the query norms)
   const float* inv_norm;    // [n] or null
-  const uint32_t* mask;     // shared bit mask or null
+  const uint32_t* mask;     // bit mask or null; query q uses the words at mask + q * mask_stride (0 = one shared mask)
+  int64_t mask_stride;
   uint64_t* cand;           // [grid, 256, kDtCap] candidate keys
   float* list_scores;       // [ranges, nq, k]
   int64_t* list_ids;        // [ranges, nq, k]
@@ -108,9 +109,11 @@ __global__ void __launch_bounds__(kDtThreads, 1)
 
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const int range = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, mgroup = blockIdx.y;
-  const int t0 = (int)(((int64_t)p.tiles_total * range) / p.num_ranges);
-  const int t1 = (int)(((int64_t)p.tiles_total * (range + 1)) / p.num_ranges);
-  const int ntiles = t1 - t0;
+  // Range r takes corpus tiles r, r + R, r + 2R, ...: at any moment all ranges — and the query groups of each, which
+  // walk the same tiles — are inside one window of R consecutive tiles, so a tile is fetched from DRAM once and
+  // served to the other query groups out of L2 even when they drift a few rounds apart (contiguous ranges let the
+  // four groups of a range drift by more than the L2 holds: 2.4x DRAM re-reads, profiles/r01_dense_tc5_v2_ncu.txt).
+  const int ntiles = (p.tiles_total - range + p.num_ranges - 1) / p.num_ranges;
   const int q0 = mgroup * (kDtMT * 128) + (PAIR ? (int)rank * 128 : 0);
   // active 128-query tiles: a pair always runs its one M = 256 MMA (rows past nq are TMA zero fill)
   const int n_act = PAIR ? 1 : min(kDtMT, (p.nq - q0 + 127) / 128);
@@ -169,7 +172,8 @@ __global__ void __launch_bounds__(kDtThreads, 1)
       else
         asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));    // queries: re-read per tile
       int it = 0;
-      for (int t = t0; t < t1; ++t) {
+      for (int ti = 0; ti < ntiles; ++ti) {
+        const int t = range + ti * p.num_ranges;
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (uint32_t)(it / kStages) & 1u;
@@ -309,7 +313,7 @@ __global__ void __launch_bounds__(kDtThreads, 1)
         mbar_wait(&acc_full[b], (uint32_t)use & 1u);
         tc5_fence_after();
         const uint32_t taddr = tlane + (uint32_t)(dbuf ? b : set) * kDtBN;
-        const int64_t row_base = (int64_t)(t0 + t) * kDtBN;
+        const int64_t row_base = (int64_t)(range + t * p.num_ranges) * kDtBN;
         auto consume = [&](uint32_t (&v)[32], int ch) {
           const int64_t r0 = row_base + ch * 32;
           if (r0 >= p.n) return;  // uniform
@@ -331,7 +335,7 @@ __global__ void __launch_bounds__(kDtThreads, 1)
           const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
           if (__any_sync(0xFFFFFFFFu, valid && m > thr)) {
             uint32_t bits = (p.n - r0 >= 32) ? 0xFFFFFFFFu : ((1u << (int)(p.n - r0)) - 1u);
-            if (p.mask) bits &= __ldg(p.mask + (r0 >> 5));
+            if (p.mask) bits &= __ldg(p.mask + (size_t)(valid ? query : 0) * p.mask_stride + (r0 >> 5));
             if (valid && m > thr) {
               float cbest = -CUDART_INF_F;
 #pragma unroll
@@ -447,7 +451,7 @@ bool tc5_dense_supported(const Tc5State* s, int64_t n, int d, int nq, int k, con
   if (nq < min_nq || n < kDtBN) return false;
   if (d % kDtBK != 0 || d < kDtBK) return false;
   if (k > 128) return false;
-  if (mask_stride_words != 0) return false;      // one shared filter for the batch
+  (void)mask_stride_words;                       // a filter per query is a per-thread mask word in the epilogue
   if (n >= (1ll << 31) * (int64_t)1) return false;
   return true;
 }
@@ -457,7 +461,7 @@ cudaError_t launch_topk_merge(const float* scores, const int64_t* ids, int nlist
                               cudaStream_t stream);
 
 int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype, const float* inv_norm, int metric,
-                   const void* queries, int nq, const uint32_t* mask, int k, int64_t id_base, float* out_scores,
+                   const void* queries, int nq, const uint32_t* mask, int64_t mask_stride_words, int k, int64_t id_base, float* out_scores,
                    int64_t* out_ids, cudaStream_t stream, int* launched, std::string* err) {
   *launched = 0;
   const int num_sms = tc5_num_sms(s);
@@ -497,6 +501,7 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
   kp.queries = queries;
   kp.inv_norm = metric == 1 ? inv_norm : nullptr;
   kp.mask = mask;
+  kp.mask_stride = mask_stride_words;
   kp.cand = reinterpret_cast<uint64_t*>(ws);
   kp.list_scores = reinterpret_cast<float*>(ws + cand_bytes);
   kp.list_ids = reinterpret_cast<int64_t*>(ws + cand_bytes + ls_bytes);

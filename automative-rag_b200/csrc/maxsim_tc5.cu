@@ -82,8 +82,13 @@ struct TcSeg {
   int g, d0, d1;
 };
 
-// wait + cycles spent waiting (the counters are written out only when a trace buffer is attached)
-__device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, long long& acc) {
+// wait (+ cycles spent waiting, only when a trace buffer is attached: two clock reads per wait are not free for the
+// single MMA-issuing thread)
+__device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, long long& acc, bool tracing) {
+  if (!tracing) {
+    mbar_wait(bar, parity);
+    return;
+  }
   const long long t = clock64();
   mbar_wait(bar, parity);
   acc += clock64() - t;
@@ -178,6 +183,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   float* parts = reinterpret_cast<float*>(segs + kTcMaxSegs);        // [2 sets][2 buffers][4 quarters] partial sums (lq > 32)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool tracing = p.trace != nullptr;
 
   if (warp == 0 && lane == 0) {
     mbar_init(a_full, 1);
@@ -273,7 +279,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         for (int t = 0; t < ntiles; ++t, ++j) {
           const int s = j % kTcStages;
           const uint32_t ph = (uint32_t)(j / kTcStages) & 1u;
-          timed_wait(&b_empty[s], ph ^ 1u, w_be);
+          timed_wait(&b_empty[s], ph ^ 1u, w_be, tracing);
           if (rank == 0 && lane == 0) mbar_arrive_expect_tx(&b_full[s], 2u * kBBytes);
           tma_load_2d_cta2(smB + s * kBBytes + kh * kBBytesKH + half * kBoxBytes, &map_d, kh * 64,
                            tok0 + t * kTcTile + half * kTcBN + (int)rank * 64, mapa_u32(smem_u32(&b_full[s]), 0), pol);
@@ -285,48 +291,67 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
-    if (lane == 0 && rank == 0 && nseg > 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA)
+    // The whole warp runs the loop with uniform control flow and lane 0 issues (predicated): the shared-memory
+    // descriptors then live in uniform registers.  With `if (lane == 0)` around the loop every tcgen05.mma cost 10-12
+    // instructions (64-bit adds + four R2UR moves) and the 163 instructions per 512-cycle MMA group made this ONE
+    // thread, not the tensor cores, the pace of the kernel (profiles/r02_maxsim_trace_v6.txt: 654 cycles per group).
+    if (rank == 0 && nseg > 0) {
       constexpr uint32_t idesc = umma_idesc_f16(BF16, 256, kTcBN);
       int j = 0;
-      int uses[kTcSlots] = {0, 0, 0, 0};  // slot uses so far (phase of acc_empty / acc_full)
+      int uses0 = 0, uses1 = 0;  // uses of the slots of pair tile 0 / 1 so far (phase of acc_empty / acc_full)
       const long long T0 = clock64();
       long long w_bf = 0, w_ae = 0, w_af = 0;
+      // Descriptors are built once: the address field (bits [0,14) = byte address >> 4) of a tile at another offset is
+      // the base descriptor plus offset >> 4 (all of shared memory is below 2^18 bytes).
+      const uint64_t desc_a0 = umma_smem_desc_sw128(smem_u32(smA));
+      const uint64_t desc_b0 = umma_smem_desc_sw128(smem_u32(smB));
       for (int si = 0; si < nseg; ++si) {
         const TcSeg sg = segs[si];
         const int n_act = min(kTcMG, p.num_pair_tiles - sg.g * kTcMG);
         const int tok0 = __ldg(p.doc_offsets + sg.d0);
         const int ntiles = (__ldg(p.doc_offsets + sg.d1) - tok0 + kTcTile - 1) / kTcTile;
-        timed_wait(a_full, (uint32_t)si & 1u, w_af);
+        timed_wait(a_full, (uint32_t)si & 1u, w_af, tracing);
         for (int t = 0; t < ntiles; ++t, ++j) {
           const int s = j % kTcStages;
           const uint32_t ph = (uint32_t)(j / kTcStages) & 1u;
-          timed_wait(&b_full[s], ph, w_bf);
+          timed_wait(&b_full[s], ph, w_bf, tracing);
           tc5_fence_after();
+          const uint64_t desc_bs = desc_b0 + (uint64_t)((uint32_t)s * (kBBytes >> 4));
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            for (int a = 0; a < n_act; ++a) {
-              const int slot = a * 2 + half;
-              timed_wait(&acc_empty[slot], ((uint32_t)uses[slot] & 1u) ^ 1u, w_ae);
-              ++uses[slot];
-              tc5_fence_after();
 #pragma unroll
-              for (int kh = 0; kh < KH; ++kh) {
-                const uint64_t da = umma_smem_desc_sw128(smem_u32(smA + a * kABytes + kh * kABytesKH));
-                const uint64_t db = umma_smem_desc_sw128(smem_u32(smB + s * kBBytes + kh * kBBytesKH + half * kBoxBytes));
+            for (int a = 0; a < kTcMG; ++a) {
+              if (a < n_act) {
+                constexpr int kDummy = 0;
+                (void)kDummy;
+                const int slot = a * 2 + half;
+                timed_wait(&acc_empty[slot], ((uint32_t)(a == 0 ? uses0 : uses1) & 1u) ^ 1u, w_ae, tracing);
+                tc5_fence_after();
+                if (elect_one_sync()) {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)  // 4 x UMMA_K(16 elements = 32 B) per 128-byte swizzle row
-                  umma_f16_ss_cta2(tmem_base + (uint32_t)slot * kTcBN, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
-                                   (kh | kk) != 0 ? 1u : 0u);
+                  for (int kh = 0; kh < KH; ++kh) {
+                    const uint64_t da = desc_a0 + (uint64_t)((a * kABytes + kh * kABytesKH) >> 4);
+                    const uint64_t db = desc_bs + (uint64_t)((kh * kBBytesKH + half * kBoxBytes) >> 4);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)  // 4 x UMMA_K(16 elements = 32 B) per 128-byte swizzle row
+                      umma_f16_ss_cta2(tmem_base + (uint32_t)slot * kTcBN, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2),
+                                       idesc, (kh | kk) != 0 ? 1u : 0u);
+                  }
+                  umma_commit_cta2(&acc_full[slot], 0b11);  // slot ready for its epilogue set in both CTAs
+                  if (half == 1 && a == n_act - 1) umma_commit_cta2(&b_empty[s], 0b11);  // stage reusable (both CTAs)
+                }
+                __syncwarp();
               }
-              umma_commit_cta2(&acc_full[slot], 0b11);  // slot ready for its epilogue set in both CTAs
             }
           }
-          umma_commit_cta2(&b_empty[s], 0b11);  // B stage reusable (both CTAs) once the MMAs have read it
+          ++uses0;
+          uses1 += n_act > 1 ? 1 : 0;
         }
-        umma_commit_cta2(a_empty, 0b11);  // query tiles reusable once every MMA of the segment has completed
+        if (elect_one_sync()) umma_commit_cta2(a_empty, 0b11);  // query tiles reusable once the segment's MMAs are done
+        __syncwarp();
       }
-      if (p.trace) {
+      if (p.trace && lane == 0) {
         p.trace[blockIdx.x * 16 + 0] = clock64() - T0;
         p.trace[blockIdx.x * 16 + 1] = w_bf;
         p.trace[blockIdx.x * 16 + 2] = w_ae;
@@ -448,7 +473,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll 1
       for (int h = 0; h < 2 * ntiles; ++h, ++use) {  // half-tiles of 128 tokens, in token order
         const int half = use & 1;
-        timed_wait(&acc_full[set * 2 + half], (uint32_t)(use >> 1) & 1u, w_full);
+        timed_wait(&acc_full[set * 2 + half], (uint32_t)(use >> 1) & 1u, w_full, tracing);
         tc5_fence_after();
         const uint32_t taddr = tlane + (uint32_t)half * kTcBN;
         const int cbase = h * kTcBN;

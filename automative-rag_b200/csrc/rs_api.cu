@@ -49,6 +49,11 @@ struct rs_handle {
   float* shard_scores = nullptr;  // local top-k of rs_dense_topk_sharded_host before the exchange
   int64_t* shard_ids = nullptr;
   size_t shard_pairs = 0;
+  // per-call statistics (rs_set_profiling)
+  bool profiling = false;
+  cudaEvent_t prof_ev[3] = {nullptr, nullptr, nullptr};  // start, before the merge launch, end
+  bool prof_mid = false, prof_pending = false;
+  rs_call_stats prof{};
   int dense_impl = RS_DENSE_AUTO, maxsim_impl = RS_MAXSIM_AUTO;
   int last_dense_impl = 0, last_maxsim_impl = 0;
   int64_t launches = 0;
@@ -133,6 +138,32 @@ int ensure_staging(rs_handle* h, size_t host_bytes, size_t dev_bytes) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Bracket of one profiled call: the constructor records the start event, finish() the end event and the counters.
+struct ProfScope {
+  rs_handle* h;
+  cudaStream_t st;
+  int64_t launches0;
+  bool on;
+  ProfScope(rs_handle* handle, cudaStream_t stream) : h(handle), st(stream), launches0(handle->launches), on(handle->profiling) {
+    if (on) {
+      cudaEventRecord(h->prof_ev[0], st);
+      h->prof_mid = false;
+    }
+  }
+  void finish(int entry, int family, int queries, int64_t bytes, double flops) {
+    if (!on) return;
+    cudaEventRecord(h->prof_ev[2], st);
+    h->prof = rs_call_stats{};
+    h->prof.entry = entry;
+    h->prof.kernel_family = family;
+    h->prof.launches = (int32_t)(h->launches - launches0);
+    h->prof.queries = queries;
+    h->prof.bytes_scanned = bytes;
+    h->prof.flops = flops;
+    h->prof_pending = true;
+  }
+};
+
 }  // namespace
 
 extern "C" {
@@ -195,6 +226,8 @@ int rs_destroy(rs_handle* h) {
   if (h->dev_stage) cudaFree(h->dev_stage);
   if (h->filt_dev) cudaFree(h->filt_dev);
   if (h->order_ev) cudaEventDestroy(h->order_ev);
+  for (cudaEvent_t ev : h->prof_ev)
+    if (ev) cudaEventDestroy(ev);
   delete h;
   return RS_OK;
 }
@@ -222,6 +255,33 @@ int rs_scan_plan(int32_t d, int32_t k, int64_t* out7) {
   rs::scan_plan_query(d, k, out7);
   return RS_OK;
 }
+int rs_set_profiling(rs_handle* h, int on) {
+  if (!h) return RS_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  if (on && !h->prof_ev[0]) {
+    for (cudaEvent_t& ev : h->prof_ev) {
+      cudaError_t e = cudaEventCreate(&ev);
+      if (e != cudaSuccess) return cuda_fail(h, e, "rs_set_profiling: cudaEventCreate");
+    }
+  }
+  h->profiling = on != 0;
+  h->prof_pending = false;
+  return RS_OK;
+}
+int rs_last_call_stats(rs_handle* h, rs_call_stats* out) {
+  if (!h || !out) return RS_ERR_INVALID_ARG;
+  if (!h->prof_pending) return fail(h, RS_ERR_INVALID_ARG, "rs_last_call_stats: no profiled call (rs_set_profiling(h, 1) first)");
+  DeviceGuard guard(h->device);
+  cudaError_t e = cudaEventSynchronize(h->prof_ev[2]);
+  if (e != cudaSuccess) return cuda_fail(h, e, "rs_last_call_stats: cudaEventSynchronize");
+  float ms = 0.f, mm = 0.f;
+  cudaEventElapsedTime(&ms, h->prof_ev[0], h->prof_ev[2]);
+  if (h->prof_mid) cudaEventElapsedTime(&mm, h->prof_ev[1], h->prof_ev[2]);
+  h->prof.device_ms = ms;
+  h->prof.merge_ms = mm;
+  *out = h->prof;
+  return RS_OK;
+}
 int rs_last_dense_impl(const rs_handle* h) { return h ? h->last_dense_impl : 0; }
 int rs_last_maxsim_impl(const rs_handle* h) { return h ? h->last_maxsim_impl : 0; }
 
@@ -247,19 +307,22 @@ int rs_dense_topk(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_
   DeviceGuard guard(h->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   order_after_last(h, st);
+  ProfScope prof(h, st);
+  const int64_t scan_bytes = n * (int64_t)d * 2;
 
   int impl = h->dense_impl;
   if (impl == RS_DENSE_AUTO) impl = rs::tc5_dense_supported(h->tc5, n, d, nq, k, mask, mask_stride_words) ? RS_DENSE_TCGEN05 : RS_DENSE_SCAN;
   if (impl == RS_DENSE_TCGEN05) {
     if (!rs::tc5_dense_supported(h->tc5, n, d, nq, k, mask, mask_stride_words))
-      return fail(h, RS_ERR_UNSUPPORTED, "rs_dense_topk: tcgen05 batched path needs nq >= 4, n >= 256, d %% 64 == 0, k <= 128, one shared mask");
+      return fail(h, RS_ERR_UNSUPPORTED, "rs_dense_topk: tcgen05 batched path needs nq >= 4, n >= 256, d %% 64 == 0, k <= 128");
     int launched = 0;
     std::string err;
-    int rc = rs::tc5_dense_topk(h->tc5, corpus, n, d, dtype, inv_norm, metric, queries, nq, mask, k, id_base, out_scores,
+    int rc = rs::tc5_dense_topk(h->tc5, corpus, n, d, dtype, inv_norm, metric, queries, nq, mask, mask_stride_words, k, id_base, out_scores,
                                 out_ids, st, &launched, &err);
     h->launches += launched;
     h->last_dense_impl = RS_DENSE_TCGEN05;
     if (rc != RS_OK) return fail(h, rc, "rs_dense_topk(tcgen05): %s", err.c_str());
+    prof.finish(RS_CALL_DENSE_TOPK, RS_DENSE_TCGEN05, nq, scan_bytes, 2.0 * nq * (double)n * d);
     return RS_OK;
   }
 
@@ -288,6 +351,7 @@ int rs_dense_topk(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_
     if (e != cudaSuccess) return cuda_fail(h, e, "dense_scan_kernel launch");
     h->launches += 1;
   }
+  prof.finish(RS_CALL_DENSE_TOPK, RS_DENSE_SCAN, nq, scan_bytes * nq, 2.0 * nq * (double)n * d);
   return RS_OK;
 }
 
@@ -368,6 +432,10 @@ int rs_maxsim(rs_handle* h, const void* q, int32_t nq, int32_t lq, int32_t d, in
   DeviceGuard guard(h->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   order_after_last(h, st);
+  ProfScope prof(h, st);
+  const double pair_tokens = (double)nq * ndo * ((double)n_tokens / (nd > 0 ? nd : 1));  // (query, document) token pairs
+  const double ms_flops = 2.0 * pair_tokens * lq * d;
+  const int64_t ms_bytes = (int64_t)((cand ? pair_tokens : (double)n_tokens) * d * (dtype == RS_F32 ? 4 : 2));
   rs::MaxSimParams p{q, q_weight, doc_tokens, doc_offsets, cand, out_scores, out_argmax, out_tokmax, n_tokens, nq, lq, d, nd, nc};
 
   if (dtype == RS_F32) {
@@ -379,6 +447,7 @@ int rs_maxsim(rs_handle* h, const void* q, int32_t nq, int32_t lq, int32_t d, in
     if (e != cudaSuccess) return cuda_fail(h, e, "maxsim_simt_kernel launch");
     h->launches += 1;
     h->last_maxsim_impl = RS_MAXSIM_SIMT;
+    prof.finish(RS_CALL_MAXSIM, RS_MAXSIM_SIMT, nq, ms_bytes, ms_flops);
     return RS_OK;
   }
   if (h->maxsim_impl == RS_MAXSIM_SIMT) return fail(h, RS_ERR_UNSUPPORTED, "rs_maxsim: SIMT path takes fp32 inputs only");
@@ -403,6 +472,7 @@ int rs_maxsim(rs_handle* h, const void* q, int32_t nq, int32_t lq, int32_t d, in
     h->launches += launched;
     h->last_maxsim_impl = RS_MAXSIM_TCGEN05;
     if (rc != RS_OK) return fail(h, rc, "rs_maxsim(tcgen05): %s", err.c_str());
+    prof.finish(RS_CALL_MAXSIM, RS_MAXSIM_TCGEN05, nq, ms_bytes, ms_flops);
     return RS_OK;
   }
   if (impl == RS_MAXSIM_TCGEN05_CAND) {
@@ -415,6 +485,7 @@ int rs_maxsim(rs_handle* h, const void* q, int32_t nq, int32_t lq, int32_t d, in
     h->launches += launched;
     h->last_maxsim_impl = RS_MAXSIM_TCGEN05_CAND;
     if (rc != RS_OK) return fail(h, rc, "rs_maxsim(tcgen05 candidates): %s", err.c_str());
+    prof.finish(RS_CALL_MAXSIM, RS_MAXSIM_TCGEN05_CAND, nq, ms_bytes, ms_flops);
     return RS_OK;
   }
   if ((d % 16) != 0) return fail(h, RS_ERR_UNSUPPORTED, "rs_maxsim: d must be a multiple of 16 for fp16/bf16 (got %d)", d);
@@ -425,6 +496,7 @@ int rs_maxsim(rs_handle* h, const void* q, int32_t nq, int32_t lq, int32_t d, in
   if (e != cudaSuccess) return cuda_fail(h, e, "maxsim_mma_kernel launch");
   h->launches += 1;
   h->last_maxsim_impl = RS_MAXSIM_MMA;
+  prof.finish(RS_CALL_MAXSIM, RS_MAXSIM_MMA, nq, ms_bytes, ms_flops);
   return RS_OK;
 }
 

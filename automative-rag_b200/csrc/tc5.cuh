@@ -67,6 +67,19 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  
 __device__ __forceinline__ void tc5_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc5_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a converged warp.  Code under `if (elect_one_sync())` is single-threaded by construction, which lets
+// ptxas keep descriptors and addresses in uniform registers (a `lane == 0` test does not: every tcgen05.mma then
+// needs R2UR moves and an ELECT loop around it).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xFFFFFFFF;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
 __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -100,8 +113,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {  // arrive on a (possibly remote) barrier
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// Arrive on a (possibly remote) barrier of the cluster.  Deliberately NOT `.release.cluster`: that form compiles to
+// MEMBAR.ALL.GPU + ERRBAR and cost the MaxSim epilogue a quarter of all its stall samples
+// (profiles/r02_maxsim_tc5_v5_ncu.txt).  The hand-off of a TMEM accumulator needs no memory ordering beyond what
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync already give; this is the form CUTLASS's
+// ClusterBarrier::arrive(cta_id) uses.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA tile load into THIS CTA's shared memory whose bytes are counted on a barrier of either CTA of the pair
 __device__ __forceinline__ void tma_load_2d_cta2(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr,

@@ -839,7 +839,8 @@ def extra_config5(cx):
             # (ii) threshold check on >= 1M sampled non-returned rows of this shard (1024 random blocks of 1024 rows)
             nblk, blk_rows = 1024, 1024
             rng = np.random.default_rng(1234 + rank)
-            starts = np.sort(rng.choice(max(1, (n_local - blk_rows) // blk_rows), size=min(nblk, max(1, n_local // blk_rows)), replace=False)) * blk_rows
+            population = max(1, (n_local - blk_rows) // blk_rows)
+            starts = np.sort(rng.choice(population, size=min(nblk, population), replace=False)) * blk_rows
             idx = (torch.from_numpy(starts).to(dev)[:, None] + torch.arange(blk_rows, device=dev)[None, :]).reshape(-1)
             sample = corpus[idx].cpu()
             sc_cpu = cpu_scores(sample, qf)

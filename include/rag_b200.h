@@ -125,6 +125,26 @@ int rs_last_dense_impl(const rs_handle* h);
 int rs_last_maxsim_impl(const rs_handle* h);
 
 /*
+ * Per-call statistics (the counterpart of the reference's per-request debug timing fields `search_time_ms` /
+ * `docs_per_second`, src/services/system_service.py:336-372).  Off by default; with rs_set_profiling(h, 1) every
+ * scoring entry point brackets its launches with CUDA events on the call's stream (two event records per call, no
+ * synchronisation).  rs_last_call_stats waits for the most recent profiled call to finish and reports it.
+ */
+typedef struct rs_call_stats {
+  int32_t entry;          /* RS_CALL_* of the call                                                          */
+  int32_t kernel_family;  /* RS_DENSE_* / RS_MAXSIM_* the call used (0 for the others)                      */
+  int32_t launches;       /* kernels launched by the call                                                   */
+  int32_t queries;        /* nq of the call                                                                 */
+  int64_t bytes_scanned;  /* algorithmic bytes: corpus rows (dense) / document tokens (MaxSim) the call reads */
+  double flops;           /* 2*M*N*K of the call                                                             */
+  float device_ms;        /* device time from the call's first launch to the end of its last                */
+  float merge_ms;         /* of which the merge of the per-range lists (batched dense) or 0                 */
+} rs_call_stats;
+enum { RS_CALL_NONE = 0, RS_CALL_DENSE_TOPK = 1, RS_CALL_MAXSIM = 2, RS_CALL_TOPK_MERGE = 3, RS_CALL_ALLGATHER_TOPK = 4 };
+int rs_set_profiling(rs_handle* h, int on);
+int rs_last_call_stats(rs_handle* h, rs_call_stats* out);
+
+/*
  * Exact brute-force top-k over a row-major corpus [n, d].
  *
  *   corpus      [n, d] dtype (RS_F16 | RS_BF16), 16-byte aligned, d % 8 == 0

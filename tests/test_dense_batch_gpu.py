@@ -188,3 +188,23 @@ def test_config3_reduced_rows_properties(engine):
     engine.set_dense_impl(_ffi.RS_DENSE_AUTO)
     torch.testing.assert_close(s[:4], ss, rtol=1e-3, atol=1e-6)
     assert (i[:4] == si).float().mean() > 0.99
+
+
+@pytest.mark.parametrize("nq", [5, 130, 300])
+def test_batched_with_a_filter_per_query(engine, nq):
+    """the reference sends a metadata filter per request (retrieval_tasks.py:74-79), so a batch
+    carries one mask per query ([nq, words]).  The batched tcgen05 kernel tests each query's own mask word in the
+    epilogue; every query is checked against the oracle with ITS filter, and AUTO now picks the batched kernel."""
+    n, d, k = 50_021, 256, 24
+    c, q = _case(300 + nq, n, d, nq, torch.bfloat16)
+    bits = np.stack([bernoulli_mask(1000 + j, n, [0.9, 0.3, 0.02][j % 3]) for j in range(nq)])
+    bits[1] = False
+    bits[1, [3, 999, 50_020]] = True                                    # a query with three passing rows: padded result
+    masks = torch.from_numpy(np.stack([odense.pack_mask(b).view(np.int32) for b in bits]).copy()).to(engine.device)
+    s, i = _run(engine, c, q, k, _ffi.RS_DENSE_TCGEN05, mask=masks)
+    cf, qf = c.float().numpy(), q.float().numpy()
+    for j in range(nq):
+        assert_topk_matches(s[j], i[j], odense.scores_f32(cf, qf[j]), bits[j], k)
+    assert (i[1, 3:] == -1).all()
+    engine.dense_topk(c.to(engine.device), q.to(engine.device), k, mask=masks)
+    assert engine.last_dense_impl == _ffi.RS_DENSE_TCGEN05

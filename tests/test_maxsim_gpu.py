@@ -145,7 +145,7 @@ def test_tcgen05_candidate_kernel_argmax_and_token_maxima(engine, name, dtype):
     (3, 32, 768, [256] * 12, 5),       # deployed shape with candidate lists
     (2, 32, 384, [1, 33, 129, 300], 0),  # six K blocks, one per ring stage
     (5, 64, 256, [90, 200, 31], 2),     # two warps per query, four K blocks
-    (2, 32, 1024, [140, 260], 0),       # the widest supported row
+    (2, 32, 704, [140, 260], 0),        # eleven K blocks, one per ring stage (lq_pad * d <= 24576 is the limit)
 ])
 def test_candidate_tcgen05_k_pipeline_matches_oracle(engine, nq, lq, d, lens, nc):
     """Rows wider than one shared-memory stage: the chunk is streamed K block by K block (d / 64 blocks)."""
