@@ -43,6 +43,7 @@ SIGNATURES = {
     "rs_dense_topk_host": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _I32, _P, _P, _I64, _I32, _I64, _P, _P, _P]),
     "rs_topk_merge": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I64, _I64, _P, _P, _P]),
     "rs_maxsim": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _I64, _P, _I32, _P, _I32, _P, _P, _P, _P]),
+    "rs_maxsim_list": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _I32, _I32, _P, _P]),
     "rs_rerank_postprocess": (C.c_int, [_P, _P, _P, _I32, _I32, _F, _F, _I32, _P, _P, _P]),
     "rs_filter_mask": (C.c_int, [_P, C.POINTER(_P), _I32, C.POINTER(_I32), C.POINTER(_I32), _P, _I64, _P, _P]),
     "rs_comm_export": (C.c_int, [_P, _I32, _I32, _I64, _P]),
@@ -322,6 +323,26 @@ class Engine:
         self._check(rc, "rs_maxsim")
         res = (out,) + ((arg,) if want_argmax else ()) + ((tmax,) if want_tokmax else ())
         return res if len(res) > 1 else out
+
+    def maxsim_list(self, q: torch.Tensor, docs: Sequence[torch.Tensor], compute_dtype: torch.dtype,
+                    q_weight: Optional[torch.Tensor] = None) -> List[float]:
+        """One query [lq, d] against a list of [Ld_i, d] tensors — all on the host or all on this device, one dtype —
+        scored in `compute_dtype`; returns the scores as Python floats.  One C call: staged upload, gather / convert
+        launch, rs_maxsim, results through mapped pinned memory (no torch op in between)."""
+        nd = len(docs)
+        lq, d = q.shape
+        on_host = docs[0].device.type == "cpu"
+        ptrs = (_P * nd)(*[t.data_ptr() for t in docs])
+        lens = (_I32 * nd)(*[t.shape[0] for t in docs])
+        out = (_F * nd)()
+        w = None
+        if q_weight is not None:
+            w = q_weight.detach().to("cpu", torch.float32).contiguous().view(-1)
+        rc = self._lib.rs_maxsim_list(self._h, q.data_ptr(), 1 if q.device.type == "cpu" else 0, lq, d, dtype_code(q.dtype),
+                                      dtype_code(compute_dtype), None if w is None else w.data_ptr(), ptrs, lens, nd,
+                                      1 if on_host else 0, out, _stream_ptr(self.device))
+        self._check(rc, "rs_maxsim_list")
+        return list(out)
 
     def rerank_postprocess(self, scores: torch.Tensor, other: Optional[torch.Tensor], top_k: int,
                            w_a: float = 0.8, w_b: float = 0.2):

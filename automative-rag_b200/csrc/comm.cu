@@ -11,7 +11,8 @@
 //   2. SIGNAL the last CTA to finish pushing (atomic ticket) fences at system scope and writes the call's sequence
 //             number into flag [parity][rank] of every rank (st.release.sys);
 //   3. WAIT   every CTA polls its OWN rank's flags (local memory: ld.acquire.sys) until all sources show the sequence
-//             number — a protocol error traps after 2 s instead of hanging the GPU;
+//             number — a peer that never arrives makes the kernel trap after 20 s (RS_COMM_TIMEOUT_MS) instead of
+//             hanging the GPU;
 //   4. CONSUME straight out of the local wire block: k-way merge of the gathered top-k lists (the same code as
 //             rs_topk_merge), element-wise max of score blocks, or a plain copy.
 // Parity = sequence number & 1: a rank can be at most one collective ahead of a peer (it cannot finish call s+1
@@ -21,6 +22,7 @@
 #include <cuda_runtime.h>
 #include <unistd.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -60,6 +62,7 @@ struct CommView {  // kernel argument
   int world, rank;
   unsigned long long slot_bytes;
   unsigned long long seq;
+  unsigned long long timeout_ns;  // how long a CTA waits for its peers before it traps
   unsigned* done_ctr;
 };
 
@@ -103,7 +106,7 @@ __device__ __forceinline__ void comm_wait(const CommView& c) {
     while (ld_acquire_sys(f) < c.seq + 1ull) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      if (t - t0 > 2000000000ull) __trap();  // 2 s: a peer never arrived — fail loudly, do not hang the box
+      if (t - t0 > c.timeout_ns) __trap();  // a peer never arrived — fail loudly, do not hang the box
     }
   }
   __syncthreads();
@@ -297,6 +300,10 @@ static CommView make_view(CommState* s) {
   v.rank = s->rank;
   v.slot_bytes = s->slot_bytes;
   v.seq = s->seq++;
+  // Ranks reach a collective at different times (host-side skew); 20 s covers that, a dead peer still ends in a trap
+  // (= a CUDA error on this rank) instead of a hung device.  RS_COMM_TIMEOUT_MS overrides.
+  static const unsigned long long timeout_ms = getenv("RS_COMM_TIMEOUT_MS") ? strtoull(getenv("RS_COMM_TIMEOUT_MS"), nullptr, 10) : 20000ull;
+  v.timeout_ns = timeout_ms * 1000000ull;
   v.done_ctr = s->done_ctr;
   return v;
 }

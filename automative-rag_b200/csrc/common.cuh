@@ -113,6 +113,7 @@ __device__ __forceinline__ bool named_bar_or(int id, int nthreads, bool pred) {
 // canonicalised to -inf first).
 __device__ __forceinline__ uint32_t f32_orderable(float s) {
   if (s != s) s = -INFINITY;
+  s += 0.f;  // -0.0 -> +0.0: the two compare equal everywhere else (numpy / torch / Python sorts), so they must tie here
   uint32_t u = __float_as_uint(s);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }

@@ -200,8 +200,11 @@ __global__ void __launch_bounds__(kDtThreads, 1)
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (pair: leader only)
-    if (lane == 0 && ntiles > 0 && rank == 0) {
+    // Whole warp, uniform control flow, the issuing lane picked by elect.sync: descriptors stay in uniform registers
+    // (with `if (lane == 0)` every tcgen05.mma cost ~10 instructions of 64-bit adds, R2UR moves and an ELECT loop).
+    if (ntiles > 0 && rank == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(BF16, PAIR ? 256 : 128, kDtBN);
+      const uint64_t desc0 = umma_smem_desc_sw128(smem_u32(stages));
       int it = 0;
       for (int t = 0; t < ntiles; ++t) {
         const int b = dbuf ? (t & 1) : 0;
@@ -213,27 +216,31 @@ __global__ void __launch_bounds__(kDtThreads, 1)
           const uint32_t ph = (uint32_t)(it / kStages) & 1u;
           mbar_wait(&full[s], ph);
           tc5_fence_after();
-          uint8_t* st = stages + (size_t)s * kStageBytes;
-          const uint64_t db = umma_smem_desc_sw128(smem_u32(st + kMT * kDtABytes));
-          if (PAIR) {
-            const uint64_t da = umma_smem_desc_sw128(smem_u32(st));
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_f16_ss_cta2(tmem_base + (uint32_t)b * kDtBN, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
-                               (kb | kk) != 0 ? 1u : 0u);
-            umma_commit_cta2(&empty[s], 0b11);
-          } else {
-            for (int a = 0; a < n_act; ++a) {
-              const uint64_t da = umma_smem_desc_sw128(smem_u32(st + a * kDtABytes));
+          if (elect_one_sync()) {
+            const uint64_t da0 = desc0 + (uint64_t)(((uint32_t)s * kStageBytes) >> 4);
+            const uint64_t db = da0 + (uint64_t)((kMT * kDtABytes) >> 4);
+            if (PAIR) {
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
-                umma_f16_ss(tmem_base + (uint32_t)(dbuf ? b : a) * kDtBN, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2),
-                            idesc, (kb | kk) != 0 ? 1u : 0u);
+                umma_f16_ss_cta2(tmem_base + (uint32_t)b * kDtBN, da0 + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
+                                 (kb | kk) != 0 ? 1u : 0u);
+              umma_commit_cta2(&empty[s], 0b11);
+            } else {
+              for (int a = 0; a < n_act; ++a) {
+                const uint64_t da = da0 + (uint64_t)((a * kDtABytes) >> 4);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_f16_ss(tmem_base + (uint32_t)(dbuf ? b : a) * kDtBN, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2),
+                              idesc, (kb | kk) != 0 ? 1u : 0u);
+              }
+              umma_commit(&empty[s]);
             }
-            umma_commit(&empty[s]);
+            if (kb == kblocks - 1) {
+              if (PAIR) umma_commit_cta2(&acc_full[b], 0b11); else umma_commit(&acc_full[b]);
+            }
           }
+          __syncwarp();
         }
-        if (PAIR) umma_commit_cta2(&acc_full[b], 0b11); else umma_commit(&acc_full[b]);
       }
     }
   } else if (warp >= 4 && warp < 4 + kEpiWarps) {

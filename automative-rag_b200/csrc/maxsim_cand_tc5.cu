@@ -155,8 +155,9 @@ __global__ void __launch_bounds__(kCdThreads, 1)
       tma_prefetch_desc(&map_d);
     }
     const uint64_t pol = cd_policy_evict_normal();
-    int64_t seq = 0;    // chunks issued so far
-    int64_t bseq = 0;   // ring stages issued so far
+    uint32_t seq = 0;   // chunks issued so far (only used modulo powers of two)
+    int rs = 0;         // ring cursor: next stage and the parity of its current use — kept incrementally, a 64-bit
+    uint32_t rph = 0;   // modulo by the run-time ring depth per stage cost the producer a third of its time
     int a_seq = -1;     // query switches so far - 1
     int cur_query = -1;
     // document bounds of pair (base + lane), fetched one batch of 32 pairs ahead of their use; a pair without tokens
@@ -223,9 +224,9 @@ __global__ void __launch_bounds__(kCdThreads, 1)
             dd.pair = pair;
           }
           const int nbox = n / kCdBox;
-          for (int st = 0; st < KB / KPS; ++st, ++bseq) {
-            const int s = (int)(bseq % S);
-            mbar_wait(&b_empty[s], ((uint32_t)(bseq / S) & 1u) ^ 1u);
+          for (int st = 0; st < KB / KPS; ++st) {
+            const int s = rs;
+            mbar_wait(&b_empty[s], rph ^ 1u);
             if (lane == 0) mbar_arrive_expect_tx(&b_full[s], (uint32_t)n * 128u * KPS);
             __syncwarp();
             if (lane < nbox * KPS) {
@@ -233,13 +234,17 @@ __global__ void __launch_bounds__(kCdThreads, 1)
               tma_load_2d(smB + (size_t)s * kStageBytes + k2 * kBlkBytes + b * kBoxBytes, &map_d, (st * KPS + k2) * 64,
                           o0 + c * per + b * kCdBox, &b_full[s], pol);
             }
+            if (++rs == S) {
+              rs = 0;
+              rph ^= 1u;
+            }
           }
         }
       }
     }
     {  // END marker: a descriptor and one (empty) ring stage
-      const int s = (int)(bseq % S);
-      mbar_wait(&b_empty[s], ((uint32_t)(bseq / S) & 1u) ^ 1u);
+      const int s = rs;
+      mbar_wait(&b_empty[s], rph ^ 1u);
       if (lane == 0) {
         ChunkDesc& dd = desc[seq % kCdDescRing];
         dd.n = 0;
@@ -255,14 +260,15 @@ __global__ void __launch_bounds__(kCdThreads, 1)
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       int a_seq = -1;
-      int64_t bseq = 0;
-      for (int64_t seq = 0;; ++seq) {
+      int rs = 0;        // ring cursor (see the producer)
+      uint32_t rph = 0;
+      for (uint32_t seq = 0;; ++seq) {
         // the first stage of the chunk (or the END marker's stage) also publishes the chunk's descriptor
-        int s = (int)(bseq % S);
-        mbar_wait(&b_full[s], (uint32_t)(bseq / S) & 1u);
+        int s = rs;
+        mbar_wait(&b_full[s], rph);
         const ChunkDesc dd = desc[seq % kCdDescRing];
         const int slot = (int)(seq % kCdSlots);
-        mbar_wait(&acc_empty[slot], ((uint32_t)(seq / kCdSlots) & 1u) ^ 1u);
+        mbar_wait(&acc_empty[slot], ((seq / kCdSlots) & 1u) ^ 1u);
         tc5_fence_after();
         if (dd.flags & kCdEnd) {
           acc_desc[slot] = dd;
@@ -279,10 +285,10 @@ __global__ void __launch_bounds__(kCdThreads, 1)
         const uint32_t idesc = (1u << 4) | ((BF16 ? 1u : 0u) << 7) | ((BF16 ? 1u : 0u) << 10) |
                                ((uint32_t)(dd.n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint8_t* At = smA + (a_seq & 1) * a_bytes;
-        for (int st = 0; st < KB / KPS; ++st, ++bseq) {
+        for (int st = 0; st < KB / KPS; ++st) {
           if (st > 0) {
-            s = (int)(bseq % S);
-            mbar_wait(&b_full[s], (uint32_t)(bseq / S) & 1u);
+            s = rs;
+            mbar_wait(&b_full[s], rph);
             tc5_fence_after();
           }
 #pragma unroll
@@ -296,6 +302,10 @@ __global__ void __launch_bounds__(kCdThreads, 1)
                           (kb | kk) != 0 ? 1u : 0u);
           }
           umma_commit(&b_empty[s]);
+          if (++rs == S) {
+            rs = 0;
+            rph ^= 1u;
+          }
         }
         acc_desc[slot] = dd;
         __threadfence_block();
@@ -334,9 +344,9 @@ __global__ void __launch_bounds__(kCdThreads, 1)
       }
     };
     uint32_t va[32], vb[32];
-    for (int64_t seq = 0;; ++seq) {
+    for (uint32_t seq = 0;; ++seq) {
       const int slot = (int)(seq % kCdSlots);
-      mbar_wait(&acc_full[slot], (uint32_t)(seq / kCdSlots) & 1u);
+      mbar_wait(&acc_full[slot], (seq / kCdSlots) & 1u);
       tc5_fence_after();
       const ChunkDesc dd = acc_desc[slot];
       if (dd.flags & kCdEnd) break;

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rag_b200.h"
@@ -39,6 +40,9 @@ struct rs_handle {
   size_t pinned_bytes = 0;
   void* dev_stage = nullptr;
   size_t dev_stage_bytes = 0;
+  // packed tokens of rs_maxsim_list (documents + query in the compute dtype)
+  void* list_buf = nullptr;
+  size_t list_buf_bytes = 0;
   // small device scratch for rs_filter_mask (values, offsets)
   int32_t* filt_dev = nullptr;
   size_t filt_dev_ints = 0;
@@ -225,6 +229,7 @@ int rs_destroy(rs_handle* h) {
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->dev_stage) cudaFree(h->dev_stage);
   if (h->filt_dev) cudaFree(h->filt_dev);
+  if (h->list_buf) cudaFree(h->list_buf);
   if (h->order_ev) cudaEventDestroy(h->order_ev);
   for (cudaEvent_t ev : h->prof_ev)
     if (ev) cudaEventDestroy(ev);
@@ -679,6 +684,118 @@ int rs_dense_topk_sharded_host(rs_handle* h, const void* corpus, int64_t n, int3
   if (e != cudaSuccess) return cuda_fail(h, e, "rs_dense_topk_sharded_host: stream synchronize");
   memcpy(out_scores_host, hp + q_bytes, (size_t)nq * k * 4);
   memcpy(out_ids_host, hp + q_bytes + os_bytes, (size_t)nq * k * 8);
+  return RS_OK;
+}
+
+// ------------------------------------------------------------------------------ MaxSim over a document LIST
+// The exact call shape of ColBERTReranker._compute_maxsim_scores (rerankers.py:215-265): one query, documents as
+// separately allocated [Ld_i, D] matrices, a list of floats back.  Everything between the caller's pointers and the
+// scores happens here: one staged upload (pointer table / offsets / weights, plus the raw tokens when they live in
+// host memory — copied into pinned memory by a few threads), one gather-and-convert launch, one rs_maxsim launch
+// writing into mapped pinned memory, one synchronise.
+int rs_maxsim_list(rs_handle* h, const void* q, int32_t q_on_host, int32_t lq, int32_t d, int32_t src_dtype,
+                   int32_t compute_dtype, const float* q_weight_host, const void* const* docs, const int32_t* doc_lens,
+                   int32_t nd, int32_t docs_on_host, float* out_scores_host, void* stream) {
+  if (!h) return RS_ERR_INVALID_ARG;
+  if (nd < 0) return fail(h, RS_ERR_INVALID_ARG, "rs_maxsim_list: negative size");
+  if (nd == 0) return RS_OK;
+  if (!q || !docs || !doc_lens || !out_scores_host) return fail(h, RS_ERR_INVALID_ARG, "rs_maxsim_list: NULL argument");
+  if (lq < 1 || d < 8 || (d % 8) != 0) return fail(h, RS_ERR_INVALID_ARG, "rs_maxsim_list: lq >= 1 and d a multiple of 8 required");
+  for (int dt : {src_dtype, compute_dtype})
+    if (dt != RS_F16 && dt != RS_BF16 && dt != RS_F32) return fail(h, RS_ERR_UNSUPPORTED, "rs_maxsim_list: bad dtype %d", dt);
+  DeviceGuard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t es = src_dtype == RS_F32 ? 4 : 2, ec = compute_dtype == RS_F32 ? 4 : 2;
+  int64_t total_rows = 0;
+  int max_len = lq;
+  for (int i = 0; i < nd; ++i) {
+    if (doc_lens[i] < 0 || !docs[i]) return fail(h, RS_ERR_INVALID_ARG, "rs_maxsim_list: document %d is NULL or has a negative length", i);
+    total_rows += doc_lens[i];
+    if (doc_lens[i] > max_len) max_len = doc_lens[i];
+  }
+  if (total_rows + lq >= (1ll << 31)) return fail(h, RS_ERR_UNSUPPORTED, "rs_maxsim_list: too many tokens");
+  // staged layout (same in pinned host memory and in the device mirror); the query travels as document nd
+  const int n_src = nd + 1;
+  const size_t o_ptr = 0, o_soff = align_up(o_ptr + (size_t)n_src * 8, 16), o_off = align_up(o_soff + (size_t)n_src * 8, 16);
+  const size_t o_w = align_up(o_off + (size_t)(n_src + 1) * 4, 16), o_raw = align_up(o_w + (size_t)lq * 4, 256);
+  size_t raw_bytes = 0;
+  std::vector<int64_t> soff(n_src, 0);
+  for (int i = 0; i < n_src; ++i) {
+    const bool on_host = i < nd ? docs_on_host != 0 : q_on_host != 0;
+    const size_t bytes = (size_t)(i < nd ? doc_lens[i] : lq) * d * es;
+    if (on_host) {
+      soff[i] = (int64_t)(o_raw + raw_bytes);
+      raw_bytes += align_up(bytes, 16);
+    }
+  }
+  const size_t in_bytes = o_raw + raw_bytes, o_out = align_up(in_bytes, 256), host_bytes = o_out + align_up((size_t)nd * 4, 256);
+  int rc = ensure_staging(h, host_bytes, in_bytes);
+  if (rc != RS_OK) return rc;
+  const size_t packed_bytes = (size_t)(total_rows + lq) * d * ec;
+  if (packed_bytes > h->list_buf_bytes) {
+    if (h->list_buf) cudaFree(h->list_buf);
+    h->list_buf = nullptr;
+    h->list_buf_bytes = 0;
+    const size_t want = packed_bytes < (4u << 20) ? (4u << 20) : packed_bytes + packed_bytes / 4;
+    cudaError_t e = cudaMalloc(&h->list_buf, want);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaMalloc(packed documents)");
+    h->list_buf_bytes = want;
+  }
+  uint8_t* hp = static_cast<uint8_t*>(h->pinned);
+  uint8_t* dp = static_cast<uint8_t*>(h->dev_stage);
+  const void** ptrs = reinterpret_cast<const void**>(hp + o_ptr);
+  int32_t* offs = reinterpret_cast<int32_t*>(hp + o_off);
+  offs[0] = 0;
+  for (int i = 0; i < n_src; ++i) {
+    ptrs[i] = i < nd ? docs[i] : q;
+    offs[i + 1] = offs[i] + (i < nd ? doc_lens[i] : lq);
+  }
+  memcpy(hp + o_soff, soff.data(), (size_t)n_src * 8);
+  if (q_weight_host) memcpy(hp + o_w, q_weight_host, (size_t)lq * 4);
+  if (q_on_host) memcpy(hp + soff[nd], q, (size_t)lq * d * es);
+  if (docs_on_host) {
+    // pageable -> pinned: a single thread copies ~10 GB/s, less than the DMA engine moves; split large lists
+    const int nthreads = raw_bytes > (2u << 20) ? 4 : 1;
+    auto copy_range = [&](int a, int b) {
+      for (int i = a; i < b; ++i) memcpy(hp + soff[i], docs[i], (size_t)doc_lens[i] * d * es);
+    };
+    if (nthreads == 1) {
+      copy_range(0, nd);
+    } else {
+      std::vector<std::thread> pool;
+      for (int t = 1; t < nthreads; ++t) pool.emplace_back(copy_range, nd * t / nthreads, nd * (t + 1) / nthreads);
+      copy_range(0, nd / nthreads);
+      for (auto& t : pool) t.join();
+    }
+  }
+  cudaError_t e = cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return cuda_fail(h, e, "H2D(document list)");
+  order_after_last(h, st);
+  // documents and the query are never mixed host / device in one table: two launches when they differ
+  const bool same_side = (docs_on_host != 0) == (q_on_host != 0);
+  auto gather = [&](int first, int count, bool on_host) {
+    return rs::launch_gather_docs(on_host ? nullptr : reinterpret_cast<const void* const*>(dp + o_ptr) + first, on_host ? dp : nullptr,
+                                  reinterpret_cast<const int64_t*>(dp + o_soff) + first, reinterpret_cast<const int32_t*>(dp + o_off) + first,
+                                  count, max_len, d, src_dtype, compute_dtype, h->list_buf, st);
+  };
+  if (same_side) {
+    e = gather(0, n_src, docs_on_host != 0);
+    h->launches += 1;
+  } else {
+    e = gather(0, nd, docs_on_host != 0);
+    if (e == cudaSuccess) e = gather(nd, 1, q_on_host != 0);
+    h->launches += 2;
+  }
+  if (e != cudaSuccess) return cuda_fail(h, e, "gather_docs_kernel launch");
+  const uint8_t* packed = static_cast<const uint8_t*>(h->list_buf);
+  float* out_dev = reinterpret_cast<float*>(static_cast<uint8_t*>(h->pinned_dev) + o_out);
+  rc = rs_maxsim(h, packed + (size_t)total_rows * d * ec, 1, lq, d, compute_dtype,
+                 q_weight_host ? reinterpret_cast<const float*>(dp + o_w) : nullptr, packed, total_rows > 0 ? total_rows : 1,
+                 reinterpret_cast<const int32_t*>(dp + o_off), nd, nullptr, 0, out_dev, nullptr, nullptr, stream);
+  if (rc != RS_OK) return rc;
+  e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(h, e, "rs_maxsim_list: stream synchronize");
+  memcpy(out_scores_host, hp + o_out, (size_t)nd * 4);
   return RS_OK;
 }
 

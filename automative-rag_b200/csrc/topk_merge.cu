@@ -194,3 +194,57 @@ cudaError_t launch_filter_mask(const int32_t* const* cols_host, int nclauses, co
 }
 
 }  // namespace rs
+
+// ------------------------------------------------------------------------- document list -> packed tokens
+// ColBERTReranker._compute_maxsim_scores receives its documents as a Python LIST of separately allocated [Ld_i, D]
+// tensors (rerankers.py:215-217); rs_maxsim wants one packed [sum Ld, D] buffer.  One launch copies (and converts to
+// the compute dtype) every document: CTA (x, i) handles rows 32x .. 32x+31 of document i, 16 bytes of source per
+// thread step, fully coalesced.  Sources are device pointers from a table (documents already on the GPU) or offsets
+// into one staged upload (documents that came from host memory).
+namespace rs {
+
+__device__ __forceinline__ float load_as_float(const void* p, int dtype, size_t i) {
+  if (dtype == 2) return reinterpret_cast<const float*>(p)[i];
+  if (dtype == 0) return __half2float(reinterpret_cast<const __half*>(p)[i]);
+  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+__device__ __forceinline__ void store_from_float(void* p, int dtype, size_t i, float v) {
+  if (dtype == 2) reinterpret_cast<float*>(p)[i] = v;
+  else if (dtype == 0) reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
+  else reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+}
+
+__global__ void __launch_bounds__(256) gather_docs_kernel(const void* const* __restrict__ ptrs,
+                                                          const uint8_t* __restrict__ staged,
+                                                          const int64_t* __restrict__ src_off,
+                                                          const int32_t* __restrict__ offsets, int d, int src_dtype,
+                                                          int dst_dtype, void* __restrict__ dst) {
+  const int doc = blockIdx.y;
+  const int row0 = offsets[doc], rows = offsets[doc + 1] - row0;
+  const int r_begin = blockIdx.x * 32;
+  if (r_begin >= rows) return;
+  const int r_end = min(rows, r_begin + 32);
+  const void* src = ptrs ? ptrs[doc] : static_cast<const void*>(staged + src_off[doc]);
+  const size_t e0 = (size_t)r_begin * d, e1 = (size_t)r_end * d;
+  const size_t esz_s = src_dtype == 2 ? 4 : 2, esz_d = dst_dtype == 2 ? 4 : 2;
+  uint8_t* out = static_cast<uint8_t*>(dst) + (size_t)row0 * d * esz_d;
+  if (src_dtype == dst_dtype && ((reinterpret_cast<uintptr_t>(src) | (size_t)d * esz_s) & 15u) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(src) + e0 * esz_s);
+    uint4* d4 = reinterpret_cast<uint4*>(out + e0 * esz_d);
+    const size_t n16 = (e1 - e0) * esz_s / 16;
+    for (size_t i = threadIdx.x; i < n16; i += blockDim.x) d4[i] = s4[i];
+  } else {
+    for (size_t i = e0 + threadIdx.x; i < e1; i += blockDim.x) store_from_float(out, dst_dtype, i, load_as_float(src, src_dtype, i));
+  }
+}
+
+cudaError_t launch_gather_docs(const void* const* ptrs_dev, const uint8_t* staged_dev, const int64_t* src_off_dev,
+                               const int32_t* offsets_dev, int nd, int max_len, int d, int src_dtype, int dst_dtype,
+                               void* dst, cudaStream_t stream) {
+  if (nd <= 0 || max_len <= 0) return cudaSuccess;
+  dim3 grid((max_len + 31) / 32, nd);
+  gather_docs_kernel<<<grid, 256, 0, stream>>>(ptrs_dev, staged_dev, src_off_dev, offsets_dev, d, src_dtype, dst_dtype, dst);
+  return cudaGetLastError();
+}
+
+}  // namespace rs

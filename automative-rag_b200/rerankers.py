@@ -159,8 +159,33 @@ class B200ColBERTReranker:
         q = query_embeddings
         if q.dim() == 3 and q.size(0) != 1:
             raise ValueError("_compute_maxsim_scores takes one query ([Lq, D] or [1, Lq, D])")
+        fast = self._list_call(q, doc_embeddings_list)
+        if fast is not None:
+            return fast
         scores = self._maxsim_device(q, doc_embeddings_list)
         return scores[0].tolist()
+
+    def _list_call(self, q: torch.Tensor, docs: Sequence[torch.Tensor]) -> Optional[List[float]]:
+        """The reference's call shape in ONE C call (rs_maxsim_list) when the list is uniform: every document a
+        contiguous [Ld, D] tensor of the query's dtype, all on the host or all on the engine's GPU.  Anything else
+        (mixed devices / dtypes, [1, Ld, D] entries, views) takes the general pack-and-call path."""
+        q2 = q[0] if q.dim() == 3 else q
+        dev = self.engine.device
+        d0 = docs[0]
+        if q2.dim() != 2 or not q2.is_contiguous() or q2.dtype not in (torch.float16, torch.bfloat16, torch.float32):
+            return None
+        if q2.device.type != "cpu" and q2.device != dev:
+            return None
+        for t in docs:
+            if t.dim() != 2 or t.dtype != q2.dtype or t.device != d0.device or not t.is_contiguous() or t.shape[1] != q2.shape[1]:
+                return None
+            if t.shape[0] == 0:
+                raise ValueError("document with zero tokens")  # torch.max over an empty dim raises in the reference too
+        if d0.device.type != "cpu" and d0.device != dev:
+            return None
+        if q2.shape[1] % 8:
+            return None
+        return self.engine.maxsim_list(q2, docs, self.compute_dtype)
 
     # -- rerank tail --------------------------------------------------------------------------
     def _order(self, scores: torch.Tensor, other: Optional[torch.Tensor], top_k: Optional[int]

@@ -823,7 +823,8 @@ def extra_config5(cx):
         try:
             qf = queries[:npq].float().numpy()
             qf = qf / np.linalg.norm(qf, axis=1, keepdims=True)
-            outs = [one_query(j) for j in range(npq)]
+            # clones: at N = 1 the stage-1 lists are views into the index's wire buffer, which the next search overwrites
+            outs = [tuple(t.clone() for t in one_query(j)) for j in range(npq)]
             torch.cuda.synchronize()
             # (i) returned stage-1 scores of the ids this rank owns, recomputed on the CPU
             worst_i = 0.0

@@ -28,6 +28,9 @@
  *       (src/core/query/llm/rerankers.py:215-265): matmul :247, row-max :250,
  *       content-token sum :255-261.  `out_argmax` serves
  *       _explain_colbert_matches (rerankers.py:489-492).
+ *   rs_maxsim_list
+ *       the same function in its own call shape: one query, a Python list of per-document
+ *       tensors in, a list of floats out (rerankers.py:215-217,244-263).
  *   rs_rerank_postprocess
  *       the sort / min-max / 0.8·colbert+0.2·bge blend / [:top_k] tail of
  *       ColBERTReranker.rerank (rerankers.py:302-343,377-380).
@@ -217,6 +220,21 @@ int rs_maxsim(rs_handle* h, const void* q, int32_t nq, int32_t lq, int32_t d, in
               float* out_scores, int32_t* out_argmax, float* out_tokmax, void* stream);
 
 /*
+ * The same scoring in the exact call shape of ColBERTReranker._compute_maxsim_scores
+ * (rerankers.py:215-265): ONE query against a LIST of separately allocated document matrices, scores back
+ * in host memory.  q is [lq, d] and docs[i] is [doc_lens[i], d], all of element type src_dtype, each on
+ * the host or on this handle's device (q_on_host / docs_on_host).  The engine stages the list in one upload
+ * (raw tokens included when they are host-resident), packs and converts it to compute_dtype in one launch,
+ * scores it with rs_maxsim (RS_F32 = the exact-fp32 kernel, the reference's CPU dtype; RS_F16 = what the
+ * reference computes under autocast on CUDA) and returns after the nd scores are in out_scores_host.
+ * q_weight_host: [lq] fp32 or NULL for the reference rule.  A zero-length document scores -inf.
+ */
+int rs_maxsim_list(rs_handle* h, const void* q, int32_t q_on_host, int32_t lq, int32_t d, int32_t src_dtype,
+                   int32_t compute_dtype, const float* q_weight_host, const void* const* docs,
+                   const int32_t* doc_lens, int32_t nd, int32_t docs_on_host, float* out_scores_host,
+                   void* stream);
+
+/*
  * Rerank tail (rerankers.py:302-343): per query row of `scores` [nq, n]:
  *   order by score desc (stable: ties keep input order);
  *   if other != NULL: min-max normalise scores over the row (all-equal -> 1.0), min-max
@@ -257,7 +275,8 @@ int rs_filter_mask(rs_handle* h, const int32_t* const* cols, int32_t nclauses,
  * wire block over NVLink, raise a flag, wait for the peers' flags, consume out of local memory —
  * no NCCL, no host round trip.  Every rank must call the same collectives in the same order;
  * calls are stream-ordered like every other entry point.  A peer that never arrives makes the
- * kernel trap after 2 s (RS_ERR_CUDA on the next call) instead of hanging the device.
+ * kernel trap after 20 s (environment RS_COMM_TIMEOUT_MS; RS_ERR_CUDA on the next call) instead of
+ * hanging the device.
  * slot_bytes bounds one rank's contribution per call: nq * k_in * 12 bytes for rs_allgather_topk.
  */
 #define RS_COMM_HANDLE_BYTES 128

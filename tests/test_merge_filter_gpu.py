@@ -173,3 +173,15 @@ def test_rerank_postprocess_large_and_tied_inputs(engine, n, hybrid):
 def test_rerank_postprocess_rejects_oversized_candidate_sets(engine):
     with pytest.raises(ValueError):
         engine.rerank_postprocess(torch.zeros(1, 20000, device=engine.device), None, 10)
+
+
+def test_signed_zero_scores_tie(engine):
+    """-0.0 and +0.0 are one score: ordered by id in the merge (as numpy's lexsort does) and by input position in the
+    rerank tail (as Python's stable sort does, rerankers.py:377-380)."""
+    dev = engine.device
+    scores = np.array([[[0.5, -0.0, 0.0, -0.0, 0.0, -1.0]]], dtype=np.float32)
+    ids = np.array([[[7, 50, 40, 30, 20, 1]]], dtype=np.int64)
+    s, i = engine.topk_merge(torch.from_numpy(scores).to(dev), torch.from_numpy(ids).to(dev), 6)
+    assert i.cpu().tolist() == [[7, 20, 30, 40, 50, 1]]
+    idx, out = engine.rerank_postprocess(torch.tensor([[-0.0, 0.0, -0.0, 1.0]], device=dev), None, 4)
+    assert idx.cpu().tolist() == [[3, 0, 1, 2]]
