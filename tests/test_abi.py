@@ -146,7 +146,18 @@ def test_sass_of_the_hot_kernels_uses_the_blackwell_units():
     for k, sass in kernels("dense_scan_kernel").items():
         assert "UBLKCP" in sass and "FHFMA" in sass and "SYNCS" in sass, k      # TMA bulk copy, 16-bit x 16-bit -> fp32 FMA
     for k, sass in kernels("maxsim_tc5_kernel").items():
-        assert "UTMALDG" in sass and "UTCHMMA" in sass and "LDTM" in sass, k     # TMA tensor load, tcgen05.mma, tcgen05.ld
+        assert "UTMALDG" in sass and "UTCHMMA.2CTA" in sass and "LDTM" in sass, k    # TMA tensor load, pair tcgen05.mma, tcgen05.ld
+        assert "UTCBAR.2CTA.MULTICAST" in sass and "ELECT" in sass, k                # multicast commit, elect.sync issue block
+        # Round-2 lessons kept as invariants: the TMEM hand-off must not compile to a GPU-scope memory barrier (25 % of
+        # the epilogue's stall samples, profiles/r02_maxsim_tc5_v5_ncu.txt), a tcgen05.mma must cost a handful of issue
+        # instructions, not ten (the single issuing thread paced the kernel), and the kernel must stay small enough to
+        # keep its hot loops in the instruction cache.
+        assert sass.count("MEMBAR.ALL.GPU") <= 2, k                                  # only the two cluster barriers (start, end)
+        lines = [ln for ln in sass.splitlines() if ln.strip().startswith("/*") and ";" in ln]
+        mma = [i for i, ln in enumerate(lines) if "UTCHMMA" in ln]
+        gaps = sorted(b - a for a, b in zip(mma, mma[1:]))
+        assert gaps[len(gaps) // 2] <= 5, (k, gaps)                                  # median distance between MMAs
+        assert len(lines) < 4500, (k, len(lines))
     for k, sass in kernels("maxsim_cand_tc5_kernel").items():
         assert "UTMALDG" in sass and "UTCHMMA" in sass and "LDTM" in sass, k
     pair = [s for k, s in kernels("dense_tc5_kernel").items() if "UTCHMMA.2CTA" in s]
@@ -154,5 +165,8 @@ def test_sass_of_the_hot_kernels_uses_the_blackwell_units():
     assert len(pair) == 2 and len(single) == 2                                   # fp16 / bf16 x pair / single-CTA
     for sass in pair:
         assert "UTMALDG.2D.2CTA" in sass and "UTCBAR.2CTA.MULTICAST" in sass and "UCGABAR" in sass
+        assert sass.count("MEMBAR.ALL.GPU") <= 2
+    for k, sass in kernels("comm_allgather_topk_kernel").items():
+        assert "MEMBAR" in sass, k                                               # the system-scope fence before the flags
     for k, sass in kernels("maxsim_mma_kernel").items():
         assert "HMMA.16816" in sass, k                                           # the legacy mma.sync fallback
