@@ -524,7 +524,8 @@ def run_b200(args):
 
 
 def committed_traffic(source: str, workload: str):
-    """dram bytes per launch from profiles/<kernel>_traffic.json if it was captured from the current kernel source."""
+    """dram__bytes_read + dram__bytes_write of one launch from profiles/traffic.json (written from `ncu --set full`
+    captures of scripts/profile_kernels.py) — only while the kernel source it was captured from is unchanged."""
     import hashlib
 
     try:
@@ -692,7 +693,8 @@ def extra_config4_sharded(cx):
         "kernel": {_ffi.RS_MAXSIM_TCGEN05: "maxsim_tc5_kernel (tcgen05, CTA pairs)", _ffi.RS_MAXSIM_TCGEN05_CAND: "maxsim_cand_tc5_kernel",
                    _ffi.RS_MAXSIM_MMA: "maxsim_mma_kernel"}.get(impl_a, str(impl_a)),
         "roofline": {"bound": "tensor", "achieved": fl / ms_a / 1e9 / world, "peak": cx.tf_burst, "unit": "TFLOP/s per GPU",
-                     "frac": fl / ms_a / 1e9 / world / cx.tf_burst, "traffic": None,
+                     "frac": fl / ms_a / 1e9 / world / cx.tf_burst,
+                     "traffic": committed_traffic("maxsim_tc5.cu", "config4a") if world == 1 else None,
                      "peak_source": "measured burst" if "bf16_tflops" in cx.peaks else "fallback",
                      "note": "includes the exchange and the torch glue of the sharded step at N > 1"},
         "parity": {"sharded_equals_unsharded_bitwise": cx.all_ok(same_a), "max_rel_err_vs_cpu_oracle_2_queries": err_a,
@@ -726,7 +728,9 @@ def extra_config4_sharded(cx):
         "kernel": {_ffi.RS_MAXSIM_TCGEN05_CAND: "maxsim_cand_tc5_kernel (tcgen05, document-streaming)",
                    _ffi.RS_MAXSIM_MMA: "maxsim_mma_kernel"}.get(impl_b, str(impl_b)),
         "roofline": {"bound": "hbm", "achieved": nbytes / ms_b / 1e6 / world, "peak": cx.hbm_peak, "unit": "GB/s per GPU",
-                     "frac": nbytes / ms_b / 1e6 / world / cx.hbm_peak, "traffic": None, "peak_source": cx.peak_src,
+                     "frac": nbytes / ms_b / 1e6 / world / cx.hbm_peak,
+                     "traffic": committed_traffic("maxsim_cand_tc5.cu", "config4b") if world == 1 else None,
+                     "peak_source": cx.peak_src,
                      "note": "owner lookup of the candidate lists and the exchange are inside the timed step"},
         "parity": {"sharded_equals_unsharded_bitwise": cx.all_ok(same_b), "max_rel_err_vs_cpu_oracle_2_queries": err_b,
                    "ok": cx.all_ok(same_b and err_b < 1e-3)}}
