@@ -65,6 +65,7 @@ struct CandParams {
   int32_t nq, lq, lq_pad, nd, nc;
   int32_t kblocks;             // d / 64
   int32_t stages;              // ring depth in use
+  int32_t a_rows;              // rows of a query K block in shared memory: 128 (zero-padded) when both buffers fit, else lq_pad
 };
 
 struct ChunkDesc {
@@ -102,13 +103,14 @@ __global__ void __launch_bounds__(kCdThreads, 1)
 
   // ---- shared memory carve-up (1024-byte aligned: SWIZZLE_128B atoms)
   const int KB = p.kblocks, S = p.stages;
-  const uint32_t a_blk = (uint32_t)p.lq_pad * 128u;  // bytes of one K block of the query tile (lq_pad rows)
+  const uint32_t a_blk = (uint32_t)p.a_rows * 128u;  // bytes of one K block of the query tile
   const uint32_t a_bytes = a_blk * (uint32_t)KB;     // one query buffer
+  const uint32_t a_tx = (uint32_t)p.lq_pad * 128u * (uint32_t)KB;  // bytes TMA delivers per query (lq_pad rows per block)
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-  uint8_t* smA = sm;                        // [2][KB][lq_pad rows x 128 B]
-  uint8_t* smB = smA + 2 * a_bytes;         // [S][KPS][128 rows x 128 B]  (the tensor core's 128-row window of the last
-                                            //  query block ends inside this ring: reads of rows >= lq_pad are garbage)
+  uint8_t* smA = sm;                        // [2][KB][a_rows x 128 B]
+  uint8_t* smB = smA + 2 * a_bytes;         // [S][KPS][128 rows x 128 B]  (with a_rows < 128 the tensor core's 128-row
+                                            //  window of the last query block ends inside this ring: garbage rows)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smB + (size_t)S * kStageBytes);
   uint64_t* a_full = bars;                       // 2
   uint64_t* a_empty = a_full + 2;                // 2
@@ -142,6 +144,14 @@ __global__ void __launch_bounds__(kCdThreads, 1)
   if (warp == 2) {
     tmem_alloc(tmem_ptr, kCdTmemCols);
     tmem_relinquish();
+  }
+  if (p.a_rows == 128) {
+    // Narrow rows (d <= 192): full 128-row query tiles, rows >= lq_pad zeroed once and never touched again (TMA refreshes
+    // the first lq_pad rows).  Measured on config 4b, same box: 3.10 ms with zero padding, 3.37 ms when the tensor core's
+    // window ran over live ring data instead (profiles/r02_maxsim_cand_ab.txt).
+    for (uint32_t i = threadIdx.x * 16; i < 2 * a_bytes; i += kCdThreads * 16)
+      *reinterpret_cast<uint4*>(smA + i) = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to TMA / UMMA
   }
   tc5_fence_before();
   __syncthreads();
@@ -208,7 +218,7 @@ __global__ void __launch_bounds__(kCdThreads, 1)
             const int ab = a_seq & 1;
             if (lane == 0) {
               mbar_wait(&a_empty[ab], ((uint32_t)(a_seq >> 1) & 1u) ^ 1u);
-              mbar_arrive_expect_tx(&a_full[ab], a_bytes);
+              mbar_arrive_expect_tx(&a_full[ab], a_tx);
             }
             __syncwarp();
             for (int kb = lane; kb < KB; kb += 32)
@@ -417,9 +427,12 @@ __global__ void __launch_bounds__(kCdThreads, 1)
 // ================================================================================ host side
 static int cand_lq_pad(int lq) { return lq <= 32 ? 32 : (lq <= 64 ? 64 : (lq <= 96 ? 96 : 128)); }
 
+// rows of a query K block in shared memory: the full zero-padded 128 when both buffers fit the budget, else lq_pad
+static int cand_a_rows(int lq_pad, int d) { return (size_t)2 * 128 * d * 2 <= (size_t)kCdABudget ? 128 : lq_pad; }
+
 // ring depth that fits next to the two query buffers, or 0 when the shape does not fit at all
 static int cand_stages(int lq_pad, int d, int kps) {
-  const size_t a_bytes = (size_t)2 * lq_pad * d * 2;
+  const size_t a_bytes = (size_t)2 * cand_a_rows(lq_pad, d) * d * 2;
   if (a_bytes > (size_t)kCdABudget) return 0;
   const size_t budget = 225 * 1024 - 1024 /*alignment*/ - 2048 /*barriers, descriptors*/ - a_bytes;
   int s = (int)(budget / ((size_t)128 * 128 * kps));
@@ -476,8 +489,9 @@ int tc5_maxsim_cand(Tc5State* s, const MaxSimParams& p, int dtype, cudaStream_t 
   kp.nc = nc;
   kp.kblocks = p.d / 64;
   kp.stages = stages;
+  kp.a_rows = cand_a_rows(lq_pad, p.d);
   const bool argmax = p.out_argmax != nullptr || p.out_tokmax != nullptr;
-  const size_t smem = 1024 + (size_t)2 * lq_pad * p.d * 2 + (size_t)stages * 128 * 128 * kps + 2048;
+  const size_t smem = 1024 + (size_t)2 * kp.a_rows * p.d * 2 + (size_t)stages * 128 * 128 * kps + 2048;
   dim3 grid(grid_x);
   cudaError_t e = cudaSuccess;
 #define RS_CD_LAUNCH(BF, KPSV, AM)                                                                                          \
