@@ -25,8 +25,10 @@
 //     ranges.  Result order and tie rule are those of the scan: (score desc, id asc).
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <math_constants.h>
+#include <vector>
 
 #include "tc5.cuh"
 #include "tc5_host.h"
@@ -66,7 +68,19 @@ struct DenseTcParams {
   int32_t num_ranges, tiles_total;
   uint32_t* gthr;           // [num_ranges, nq] orderable score of each range's gm-th best row so far (0 = none yet)
   int32_t gm;               // ceil(k / num_ranges) in 1..kDtMaxGm, or 0 = no cross-CTA threshold
+  long long* trace;         // diagnostics (RS_DENSE_TRACE=1): [CTAs][16] cycles each role spent waiting, or null
 };
+
+// wait (+ cycles spent waiting when a trace buffer is attached)
+__device__ __forceinline__ void dt_timed_wait(uint64_t* bar, uint32_t parity, long long& acc, bool tracing) {
+  if (!tracing) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  const long long t = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t;
+}
 
 // warp-level bitonic sort of n (power of two, 64..512) u64 keys in shared memory, descending
 // (one warp, __syncwarp only)
@@ -134,6 +148,8 @@ __global__ void __launch_bounds__(kDtThreads, 1)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + kAccBufs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool tracing = p.trace != nullptr;
+  const int cta_linear = (int)(blockIdx.y * gridDim.x + blockIdx.x);
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
@@ -172,12 +188,14 @@ __global__ void __launch_bounds__(kDtThreads, 1)
       else
         asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));    // queries: re-read per tile
       int it = 0;
+      const long long T0 = clock64();
+      long long w_empty = 0;
       for (int ti = 0; ti < ntiles; ++ti) {
         const int t = range + ti * p.num_ranges;
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (uint32_t)(it / kStages) & 1u;
-          mbar_wait(&empty[s], ph ^ 1u);
+          dt_timed_wait(&empty[s], ph ^ 1u, w_empty, tracing);
           uint8_t* st = stages + (size_t)s * kStageBytes;
           if (PAIR) {
             // both CTAs' bytes land on the LEADER's barrier; only the leader posts the expectation
@@ -197,6 +215,10 @@ __global__ void __launch_bounds__(kDtThreads, 1)
           }
         }
       }
+      if (tracing && lane == 0) {
+        p.trace[cta_linear * 16 + 10] = w_empty;
+        p.trace[cta_linear * 16 + 11] = clock64() - T0;
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (pair: leader only)
@@ -206,15 +228,17 @@ __global__ void __launch_bounds__(kDtThreads, 1)
       constexpr uint32_t idesc = umma_idesc_f16(BF16, PAIR ? 256 : 128, kDtBN);
       const uint64_t desc0 = umma_smem_desc_sw128(smem_u32(stages));
       int it = 0;
+      const long long T0 = clock64();
+      long long w_full = 0, w_acc = 0;
       for (int t = 0; t < ntiles; ++t) {
         const int b = dbuf ? (t & 1) : 0;
         const int use = dbuf ? (t >> 1) : t;  // uses of accumulator generation b so far
-        mbar_wait(&acc_empty[b], ((uint32_t)use & 1u) ^ 1u);  // the epilogue has drained it
+        dt_timed_wait(&acc_empty[b], ((uint32_t)use & 1u) ^ 1u, w_acc, tracing);  // the epilogue has drained it
         tc5_fence_after();
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (uint32_t)(it / kStages) & 1u;
-          mbar_wait(&full[s], ph);
+          dt_timed_wait(&full[s], ph, w_full, tracing);
           tc5_fence_after();
           if (elect_one_sync()) {
             const uint64_t da0 = desc0 + (uint64_t)(((uint32_t)s * kStageBytes) >> 4);
@@ -241,6 +265,11 @@ __global__ void __launch_bounds__(kDtThreads, 1)
           }
           __syncwarp();
         }
+      }
+      if (tracing && lane == 0) {
+        p.trace[cta_linear * 16 + 0] = clock64() - T0;
+        p.trace[cta_linear * 16 + 1] = w_full;
+        p.trace[cta_linear * 16 + 2] = w_acc;
       }
     }
   } else if (warp >= 4 && warp < 4 + kEpiWarps) {
@@ -314,10 +343,12 @@ __global__ void __launch_bounds__(kDtThreads, 1)
       const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
       const uint32_t lead_acc_empty = PAIR ? mapa_u32(smem_u32(acc_empty), 0) : 0u;
       uint32_t va[32], vb[32];
+      const long long T0 = clock64();
+      long long w_accf = 0, t_compact = 0;
       for (int t = 0; t < ntiles; ++t) {
         const int b = dbuf ? (t & 1) : 0;
         const int use = dbuf ? (t >> 1) : t;
-        mbar_wait(&acc_full[b], (uint32_t)use & 1u);
+        dt_timed_wait(&acc_full[b], (uint32_t)use & 1u, w_accf, tracing);
         tc5_fence_after();
         const uint32_t taddr = tlane + (uint32_t)(dbuf ? b : set) * kDtBN;
         const int64_t row_base = (int64_t)(range + t * p.num_ranges) * kDtBN;
@@ -398,11 +429,13 @@ __global__ void __launch_bounds__(kDtThreads, 1)
         // the next tile.  Done inside the tile it sat on the critical path: the MMA restarts only when ALL
         // the warps have drained, and some warp compacts in almost every tile.
         uint32_t need = __ballot_sync(0xFFFFFFFFu, cnt > kDtCompactAt);
+        const long long tc0 = tracing ? clock64() : 0;
         while (need) {
           const int L = __ffs(need) - 1;
           need &= need - 1;
           compact_lane(L);
         }
+        if (tracing) t_compact += clock64() - tc0;
         // refresh the cross-range bound (also off the critical path; stale values are only lower, never wrong)
         if (gm > 0 && valid && (t % cross_every) == cross_every - 1) {
           uint32_t lo = 0xFFFFFFFFu;
@@ -413,6 +446,11 @@ __global__ void __launch_bounds__(kDtThreads, 1)
             thr = fmaxf(thr_local, thr_cross);
           }
         }
+      }
+      if (tracing && quarter == 0 && lane == 0 && set == 0) {
+        p.trace[cta_linear * 16 + 4] = clock64() - T0;
+        p.trace[cta_linear * 16 + 5] = w_accf;
+        p.trace[cta_linear * 16 + 6] = t_compact;
       }
       // ---- final: every query's buffer sorted, best k written as (score, id) lists of this range
       for (int L = 0; L < 32; ++L) {
@@ -531,6 +569,14 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
       return -3;
     }
   }
+  static const bool trace_on = getenv("RS_DENSE_TRACE") != nullptr;
+  static long long* trace_dev = nullptr;
+  const int n_ctas = (pair ? 2 * ranges : ranges) * mgroups;
+  if (trace_on) {
+    if (!trace_dev) cudaMalloc(&trace_dev, (size_t)1024 * 16 * sizeof(long long));
+    cudaMemsetAsync(trace_dev, 0, (size_t)1024 * 16 * sizeof(long long), stream);
+    kp.trace = n_ctas <= 1024 ? trace_dev : nullptr;
+  }
   const size_t stage_bytes = pair ? (size_t)(kDtABytes + kDtBBytes / 2) : (size_t)kDtStageBytes;
   const size_t smem = 1024 + (size_t)(pair ? kDtStagesPair : kDtStages) * stage_bytes +
                       (size_t)(pair ? 4 : 8) * kDtCap * sizeof(uint64_t) + 256;
@@ -563,6 +609,27 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
     return -3;
   }
   *launched = 1;
+  if (trace_on && kp.trace) {
+    std::vector<long long> t((size_t)n_ctas * 16);
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(t.data(), trace_dev, t.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    auto avg = [&](int slot, int rank_sel) {
+      double sum = 0;
+      int cnt = 0;
+      for (int c = 0; c < n_ctas; ++c)
+        if (!pair || rank_sel < 0 || (c & 1) == rank_sel) {
+          sum += (double)t[(size_t)c * 16 + slot];
+          ++cnt;
+        }
+      return cnt ? sum / cnt : 0.0;
+    };
+    fprintf(stderr,
+            "[dense_tc5 trace] pair %d ranges %d groups %d tiles/range %d | MMA (leader): total %.0f wait full %.0f acc_empty %.0f | "
+            "epilogue warp 4 (leader/peer): total %.0f/%.0f wait acc_full %.0f/%.0f compaction %.0f/%.0f | producer (leader/peer): "
+            "total %.0f/%.0f wait empty %.0f/%.0f  [cycles, mean over CTAs]\n",
+            (int)pair, ranges, mgroups, tiles_total / ranges, avg(0, 0), avg(1, 0), avg(2, 0), avg(4, 0), avg(4, 1), avg(5, 0),
+            avg(5, 1), avg(6, 0), avg(6, 1), avg(11, 0), avg(11, 1), avg(10, 0), avg(10, 1));
+  }
   e = launch_topk_merge(kp.list_scores, kp.list_ids, ranges, nq, k, k, 0, 0, out_scores, out_ids, stream);
   if (e != cudaSuccess) {
     *err = cudaGetErrorString(e);
