@@ -25,9 +25,11 @@
 //     ranges.  Result order and tie rule are those of the scan: (score desc, id asc).
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <math_constants.h>
+#include <type_traits>
 #include <vector>
 
 #include "tc5.cuh"
@@ -47,6 +49,7 @@ constexpr int kDtBK = 64;         // K elements per stage (one 128-byte swizzle 
 constexpr int kDtMT = 2;          // 128-query UMMA tiles per CTA (single-CTA tiles) / CTAs per pair
 constexpr int kDtStages = 3;
 constexpr int kDtStagesPair = 6;  // a pair's stage is half the size: 128 query rows + 128 corpus rows per CTA
+constexpr int kDtMaxGroups = 16;  // groups of ranges behind the cross-range bound (one batch of loads per refresh)
 constexpr int kDtMaxGm = 8;       // best scores tracked per (range, query) for the cross-range bound
 constexpr int kDtCap = 512;       // candidate buffer entries per (CTA, query): room for a whole tile (256 rows) of
                                   // appends on top of kDtCompactAt, so compaction can wait for the end of the tile
@@ -61,13 +64,19 @@ struct DenseTcParams {
   const uint32_t* mask;     // bit mask or null; query q uses the words at mask + q * mask_stride (0 = one shared mask)
   int64_t mask_stride;
   uint64_t* cand;           // [grid, 256, kDtCap] candidate keys
-  float* list_scores;       // [ranges, nq, k]
-  int64_t* list_ids;        // [ranges, nq, k]
+  float* list_scores;       // [ranges, nq, k_list]
+  int64_t* list_ids;        // [ranges, nq, k_list]
+  float* qscale_out;        // [nq] the factor the list scores carry on top of the threshold words (cosine: 1/|q|)
+  int32_t k_list;           // slots per (range, query) list, >= k
+  int32_t a_rows;           // query rows per TMA box: 128, or nq rounded up to 8 for a batch below 128 queries
   int64_t n, id_base;
   int32_t nq, d, k, metric;
   int32_t num_ranges, tiles_total;
-  uint32_t* gthr;           // [num_ranges, nq] orderable score of each range's gm-th best row so far (0 = none yet)
-  int32_t gm;               // ceil(k / num_ranges) in 1..kDtMaxGm, or 0 = no cross-CTA threshold
+  uint32_t* gthr;           // [cross_groups, nq] orderable score: max over the group's ranges of the range's gm-th
+                            // best row so far (0 = none yet)
+  int32_t gm;               // rows a range vouches for, 1..kDtMaxGm, or 0 = no cross-CTA threshold
+  int32_t bootstrap;        // 1 = bisect a first threshold out of each range's first tile (0: RS_DENSE_NO_BOOTSTRAP)
+  int32_t cross_groups;     // ceil(k / gm) <= min(num_ranges, kDtMaxGroups): the cross-CTA threshold is the minimum over these
   long long* trace;         // diagnostics (RS_DENSE_TRACE=1): [CTAs][16] cycles each role spent waiting, or null
 };
 
@@ -150,6 +159,12 @@ __global__ void __launch_bounds__(kDtThreads, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool tracing = p.trace != nullptr;
   const int cta_linear = (int)(blockIdx.y * gridDim.x + blockIdx.x);
+  long long k_c0 = 0;
+  unsigned long long k_g0 = 0;
+  if (tracing) {
+    k_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_g0));
+  }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
@@ -169,6 +184,18 @@ __global__ void __launch_bounds__(kDtThreads, 1)
       tmem_alloc(tmem_ptr, 512);
       tmem_relinquish();
     }
+  }
+  // A batch of fewer than 128 queries is staged as a box of a_rows rows: the rest of the 128-row UMMA operand is
+  // zeroed here once and never written again (the 128-byte swizzle permutes inside a row, not across rows).  Letting
+  // TMA zero-fill the missing rows of a 128-row box costs more than the copy: 0.43-0.57 ms for 3..32 queries over
+  // 1M rows where 64 queries took 0.38.
+  const uint32_t a_tx = p.a_rows < 128 ? (uint32_t)p.a_rows * 128u : (uint32_t)(PAIR ? 1 : n_act) * kDtABytes;
+  if (!PAIR && p.a_rows < 128) {
+    for (int s = 0; s < kStages; ++s) {
+      uint4* a = reinterpret_cast<uint4*>(stages + (size_t)s * kStageBytes);
+      for (int i = threadIdx.x; i < (int)(kDtABytes / 16); i += blockDim.x) a[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
   }
   tc5_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();
@@ -206,7 +233,7 @@ __global__ void __launch_bounds__(kDtThreads, 1)
             else
               tma_load_2d_cta2(st + kDtABytes, &map_c, kb * kDtBK, t * kDtBN + (int)rank * (int)kBRows, lead, pol);
           } else {
-            if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)n_act * kDtABytes + kBBytes);
+            if (lane == 0) mbar_arrive_expect_tx(&full[s], a_tx + kBBytes);
             __syncwarp((1u << nbox) - 1u);
             if (lane < nbox - 1)
               tma_load_2d(st + lane * kDtABytes, &map_q, kb * kDtBK, q0 + lane * 128, &full[s], pol);
@@ -313,10 +340,15 @@ __global__ void __launch_bounds__(kDtThreads, 1)
         for (int j = 1; j < kDtMaxGm; ++j) r = (gm == j + 1) ? tm[j] : r;
         return r;
       };
-      uint32_t* my_gthr = p.gthr + (size_t)range * p.nq + (valid ? query : 0);
-      const int cross_every = max(1, p.num_ranges / 32);  // tiles between refreshes of thr_cross
+      // this range's group: the first (ranges % G) groups hold one range more than the others
+      const int grp_base = p.num_ranges / p.cross_groups, grp_rem = p.num_ranges % p.cross_groups;
+      const int my_group = range < grp_rem * (grp_base + 1) ? range / (grp_base + 1)
+                                                            : grp_rem + (range - grp_rem * (grp_base + 1)) / grp_base;
+      uint32_t* my_gthr = p.gthr + (size_t)my_group * p.nq + (valid ? query : 0);
+      int next_refresh = 0;  // tile after which thr_cross is read again
       int cnt = 0;
       const int k = p.k;
+      const bool bootstrap = p.bootstrap != 0;
 
       // the warp sorts lane L's candidate buffer and keeps the best k
       auto compact_lane = [&](int L) {
@@ -344,7 +376,7 @@ __global__ void __launch_bounds__(kDtThreads, 1)
       const uint32_t lead_acc_empty = PAIR ? mapa_u32(smem_u32(acc_empty), 0) : 0u;
       uint32_t va[32], vb[32];
       const long long T0 = clock64();
-      long long w_accf = 0, t_compact = 0;
+      long long w_accf = 0, t_compact = 0, t_boot = 0, t_refresh = 0, t_slow = 0, n_slow = 0;
       for (int t = 0; t < ntiles; ++t) {
         const int b = dbuf ? (t & 1) : 0;
         const int use = dbuf ? (t >> 1) : t;
@@ -372,6 +404,7 @@ __global__ void __launch_bounds__(kDtThreads, 1)
           }
           const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
           if (__any_sync(0xFFFFFFFFu, valid && m > thr)) {
+            const long long ts0 = tracing ? clock64() : 0;
             uint32_t bits = (p.n - r0 >= 32) ? 0xFFFFFFFFu : ((1u << (int)(p.n - r0)) - 1u);
             if (p.mask) bits &= __ldg(p.mask + (size_t)(valid ? query : 0) * p.mask_stride + (r0 >> 5));
             if (valid && m > thr) {
@@ -401,11 +434,73 @@ __global__ void __launch_bounds__(kDtThreads, 1)
                   }
                 }
                 const float after = gm_th();
-                if (after > before) __stcg(my_gthr, f32_orderable(after));
+                if (after > before) atomicMax(my_gthr, f32_orderable(after));
               }
+            }
+            if (tracing) {
+              t_slow += clock64() - ts0;
+              ++n_slow;
             }
           }
         };
+        const long long tb0 = tracing ? clock64() : 0;
+        if (t == 0 && bootstrap) {
+          // ---- first tile of the range: find a threshold before anything is appended.  Without one every row of
+          // the tile enters the buffer and each of the warp's 32 queries pays a 256-key sort for it (~19 k cycles
+          // each: half the kernel for a 64-query batch over 1M rows).  Bisection between the tile's lowest and
+          // highest score, each step one more read of the accumulators (they stay in TMEM), all 32 queries in
+          // parallel: the largest midpoint that still leaves >= k admissible rows above it is a valid thr_local.
+          float hi = -CUDART_INF_F, lo = CUDART_INF_F, best = -CUDART_INF_F;
+          auto scan = [&](auto first_tag, float mid, float& mx, float& mn) {
+            constexpr bool FIRST = decltype(first_tag)::value;
+            int above = 0;
+#pragma unroll 1
+            for (int ch = 0; ch < kDtBN / 32; ++ch) {
+              const int64_t r0 = row_base + ch * 32;
+              if (r0 >= p.n) break;  // uniform
+              tmem_ld_32x32(taddr + ch * 32, va);
+              uint32_t bits = (p.n - r0 >= 32) ? 0xFFFFFFFFu : ((1u << (int)(p.n - r0)) - 1u);
+              if (p.mask) bits &= __ldg(p.mask + (size_t)(valid ? query : 0) * p.mask_stride + (r0 >> 5));
+              tmem_ld_wait(va);
+              if (!FIRST && !p.inv_norm && __all_sync(0xFFFFFFFFu, bits == 0xFFFFFFFFu)) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) above += __uint_as_float(va[c]) > mid ? 1 : 0;
+                continue;
+              }
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                float sc = __uint_as_float(va[c]);
+                if (p.inv_norm) sc *= (r0 + c < p.n) ? __ldg(p.inv_norm + r0 + c) : 0.f;
+                if ((bits >> c) & 1u) {
+                  above += sc > mid ? 1 : 0;
+                  if (FIRST) {
+                    mx = fmaxf(mx, sc);
+                    mn = fminf(mn, sc);
+                  }
+                }
+              }
+            }
+            return above;
+          };
+          float dummy_hi = 0.f, dummy_lo = 0.f;
+          scan(std::true_type{}, CUDART_INF_F, hi, lo);
+#pragma unroll 1
+          for (int it = 0; it < 6; ++it) {
+            const float mid = 0.5f * lo + 0.5f * hi;
+            const int above = scan(std::false_type{}, mid, dummy_hi, dummy_lo);
+            if (above >= k) {
+              best = mid;
+              lo = mid;
+            } else {
+              hi = mid;
+            }
+          }
+          if (valid && best > thr_local) {
+            thr_local = best;
+            thr = fmaxf(thr_local, thr_cross);
+          }
+          if (tracing) t_boot += clock64() - tb0;
+        }
         tmem_ld_32x32(taddr, va);
         tmem_ld_wait(va);
 #pragma unroll 1
@@ -436,49 +531,131 @@ __global__ void __launch_bounds__(kDtThreads, 1)
           compact_lane(L);
         }
         if (tracing) t_compact += clock64() - tc0;
-        // refresh the cross-range bound (also off the critical path; stale values are only lower, never wrong)
-        if (gm > 0 && valid && (t % cross_every) == cross_every - 1) {
+        // refresh the cross-range bound (also off the critical path; stale values are only lower, never wrong).
+        // The ranges form G = ceil(k / gm) <= 16 groups; a group's word is the atomic max of what its ranges
+        // published, i.e. it stands for gm rows of ONE of its ranges, so the minimum T over the groups has
+        // >= G * gm >= k distinct rows at or above it.  (Round 2 started with one word per range and the minimum
+        // over all of them: with k = 10 over 148 ranges that is the worst of 148 range maxima instead of the 10th
+        // best of group maxima — an order of magnitude more rows passed — and reading 148 words under a saturated
+        // memory system cost ~25 k cycles per refresh, more than the rest of a small batch's epilogue.)
+        if (gm > 0 && t == next_refresh) {
+          // The bound moves like 1/rows_seen: refresh after every tile at first, then at geometrically growing
+          // distances.
+          next_refresh = t + 1 + t / 8;
+          const long long tr0 = tracing ? clock64() : 0;
           uint32_t lo = 0xFFFFFFFFu;
-          const uint32_t* g = p.gthr + query;
-          for (int c = 0; c < p.num_ranges; ++c) lo = min(lo, __ldcg(g + (size_t)c * p.nq));
-          if (lo > 1u) {  // every range has published: the float just below T
+          const uint32_t* g = p.gthr + (valid ? query : 0);
+#pragma unroll
+          for (int j = 0; j < kDtMaxGroups; ++j) {  // one L2 round trip: the loads are independent
+            const uint32_t v = j < p.cross_groups ? __ldcg(g + (size_t)j * p.nq) : 0xFFFFFFFFu;
+            lo = min(lo, v);
+          }
+          if (valid && lo > 1u) {  // every group has a published value: the float just below T
             thr_cross = orderable_f32(lo - 1u);
             thr = fmaxf(thr_local, thr_cross);
           }
+          if (tracing) t_refresh += clock64() - tr0;
         }
       }
       if (tracing && quarter == 0 && lane == 0 && set == 0) {
         p.trace[cta_linear * 16 + 4] = clock64() - T0;
         p.trace[cta_linear * 16 + 5] = w_accf;
         p.trace[cta_linear * 16 + 6] = t_compact;
+        p.trace[cta_linear * 16 + 7] = t_boot;
+        p.trace[cta_linear * 16 + 8] = t_refresh;
+        p.trace[cta_linear * 16 + 9] = t_slow;
+        p.trace[cta_linear * 16 + 12] = n_slow;
       }
-      // ---- final: every query's buffer sorted, best k written as (score, id) lists of this range
-      for (int L = 0; L < 32; ++L) {
-        compact_lane(L);
-        const int qL = q0 + set * 128 + quarter * 32 + L;
-        if (qL < p.nq) {  // uniform
-          const int c = __shfl_sync(0xFFFFFFFFu, cnt, L);
-          const float sc = __shfl_sync(0xFFFFFFFFu, q_scale, L);
-          float* ls = p.list_scores + ((size_t)range * p.nq + qL) * k;
-          int64_t* li = p.list_ids + ((size_t)range * p.nq + qL) * k;
-          for (int i = lane; i < k; i += 32) {
-            if (i < c) {
-              const uint64_t key = my_sort[i];
-              ls[i] = key_score(key) * sc;
-              li[i] = p.id_base + (int64_t)key_row(key);
+      // ---- final: the range's list of every query, kl >= k slots, in NO particular order (the merge does not need
+      // one), all 32 queries of the warp at once.  A buffer that fits the list is copied as it is.  A longer one is
+      // cut by a score threshold with between k and kl keys above it, found by bisection over the buffer staged in
+      // shared memory (the pipeline stages are dead by now: the last acc_full was committed after every MMA that read
+      // them).  Only a buffer whose k-th score is tied beyond kl falls back to the warp's sort.  (Sorting every buffer,
+      // one query after the other with an L2 round trip each, was a quarter of a 64-query batch over 1M rows at
+      // k = 10 and more than half of it at k = 100.)
+      const int kl = p.k_list;
+      const bool staged = PAIR || n_act == 1;  // 4 epilogue warps x 48 KB
+      uint64_t* col = reinterpret_cast<uint64_t*>(stages) + (size_t)(warp - 4) * (kDtCompactAt * 32) + lane;
+      uint32_t cut = 0u;        // keys with score bits above this go to the list
+      bool from_global = !staged;
+      if (staged) {
+#pragma unroll 8
+        for (int i = 0; i < cnt; ++i) col[i * 32] = __ldcg(my_cand + i);
+        bool searching = valid && cnt > kl;
+        uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+        if (searching) {
+          for (int i = 0; i < cnt; ++i) {
+            const uint32_t sb = (uint32_t)(col[i * 32] >> 32);
+            lo = min(lo, sb);
+            hi = max(hi, sb);
+          }
+          lo = lo > 0u ? lo - 1u : 0u;  // every key is above lo; none is above hi
+        }
+        bool failed = false;
+        while (__any_sync(0xFFFFFFFFu, searching)) {
+          if (searching) {
+            if (hi - lo <= 1u) {
+              failed = true;
+              searching = false;
             } else {
-              ls[i] = -CUDART_INF_F;
-              li[i] = -1;
+              const uint32_t mid = lo + (hi - lo) / 2u;
+              int above = 0;
+              for (int i = 0; i < cnt; ++i) above += (uint32_t)(col[i * 32] >> 32) > mid ? 1 : 0;
+              if (above > kl) {
+                lo = mid;
+              } else if (above < k) {
+                hi = mid;
+              } else {
+                cut = mid;
+                searching = false;
+              }
             }
           }
         }
-        __syncwarp();
+        uint32_t need = __ballot_sync(0xFFFFFFFFu, failed);
+        from_global = failed;
+        while (need) {
+          const int L = __ffs(need) - 1;
+          need &= need - 1;
+          compact_lane(L);
+        }
+      } else {
+        uint32_t need = __ballot_sync(0xFFFFFFFFu, valid && cnt > kl);
+        while (need) {
+          const int L = __ffs(need) - 1;
+          need &= need - 1;
+          compact_lane(L);
+        }
+      }
+      if (valid && range == 0) p.qscale_out[query] = q_scale;
+      if (valid) {
+        float* ls = p.list_scores + ((size_t)range * p.nq + query) * kl;
+        int64_t* li = p.list_ids + ((size_t)range * p.nq + query) * kl;
+        int w = 0;
+        for (int i = 0; i < cnt; ++i) {
+          const uint64_t key = from_global ? __ldcg(my_cand + i) : col[i * 32];
+          if (from_global || (uint32_t)(key >> 32) > cut) {
+            ls[w] = key_score(key) * q_scale;
+            li[w] = p.id_base + (int64_t)key_row(key);
+            ++w;
+          }
+        }
+        for (; w < kl; ++w) {
+          ls[w] = -CUDART_INF_F;
+          li[w] = -1;
+        }
       }
     }
   }
 
   tc5_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();  // pair: the peer may still read this CTA's tiles / barriers
+  if (tracing && threadIdx.x == 0) {
+    unsigned long long g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    p.trace[cta_linear * 16 + 13] = clock64() - k_c0;
+    p.trace[cta_linear * 16 + 14] = (long long)(g1 - k_g0);
+  }
   if (warp == 2) {
     tc5_fence_after();
     if (PAIR) tmem_dealloc_cta2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
@@ -501,10 +678,6 @@ bool tc5_dense_supported(const Tc5State* s, int64_t n, int d, int nq, int k, con
   return true;
 }
 
-cudaError_t launch_topk_merge(const float* scores, const int64_t* ids, int nlists, int nq, int k_in, int k_out,
-                              int64_t score_list_stride, int64_t id_list_stride, float* out_scores, int64_t* out_ids,
-                              cudaStream_t stream);
-
 int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype, const float* inv_norm, int metric,
                    const void* queries, int nq, const uint32_t* mask, int64_t mask_stride_words, int k, int64_t id_base, float* out_scores,
                    int64_t* out_ids, cudaStream_t stream, int* launched, std::string* err) {
@@ -518,13 +691,18 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
   int ranges = (pair ? num_sms / 2 : num_sms) / mgroups;
   if (ranges < 1) ranges = 1;
   if (ranges > tiles_total) ranges = tiles_total;
-  while ((long long)ranges * k > 16384) --ranges;  // rs_topk_merge limit
+  // slots per (range, query) list: k plus slack, so that a threshold with [k, k_list] keys above it is easy to find;
+  // ranges * k_list keys per query must fit rs_topk_merge's shared memory
+  int k_list = std::max(32, k + std::max(k / 2, 22));
+  if ((long long)ranges * k_list > 16384) k_list = std::max(k, 16384 / ranges);
+  while ((long long)ranges * k_list > 16384) --ranges;
 
+  const int a_rows = nq < 128 ? (nq + 7) / 8 * 8 : 128;
   CUtensorMap map_q, map_c;
   {
     const uint64_t dims[2] = {(uint64_t)d, (uint64_t)nq};
     const uint64_t strides[1] = {(uint64_t)d * 2};
-    const uint32_t box[2] = {kDtBK, 128};
+    const uint32_t box[2] = {kDtBK, (uint32_t)a_rows};
     if (!tc5_encode(s, &map_q, dtype, 2, queries, dims, strides, box, err)) return -2;
   }
   {
@@ -534,10 +712,11 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
     if (!tc5_encode(s, &map_c, dtype, 2, corpus, dims, strides, box, err)) return -2;
   }
   const size_t cand_bytes = (size_t)ranges * mgroups * (kDtMT * 128) * kDtCap * sizeof(uint64_t);
-  const size_t ls_bytes = ((size_t)ranges * nq * k * sizeof(float) + 255) / 256 * 256;
-  const size_t li_bytes = ((size_t)ranges * nq * k * sizeof(int64_t) + 255) / 256 * 256;
-  const size_t gt_bytes = (size_t)ranges * nq * sizeof(uint32_t);
-  uint8_t* ws = static_cast<uint8_t*>(tc5_dense_scratch(s, cand_bytes + ls_bytes + li_bytes + gt_bytes));
+  const size_t ls_bytes = ((size_t)ranges * nq * k_list * sizeof(float) + 255) / 256 * 256;
+  const size_t li_bytes = ((size_t)ranges * nq * k_list * sizeof(int64_t) + 255) / 256 * 256;
+  const size_t gt_bytes = ((size_t)ranges * nq * sizeof(uint32_t) + 255) / 256 * 256;
+  const size_t qs_bytes = (size_t)nq * sizeof(float);
+  uint8_t* ws = static_cast<uint8_t*>(tc5_dense_scratch(s, cand_bytes + ls_bytes + li_bytes + gt_bytes + qs_bytes));
   if (!ws) {
     *err = "out of device memory for the candidate buffers";
     return -5;
@@ -555,13 +734,19 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
   kp.nq = nq;
   kp.d = d;
   kp.k = k;
+  kp.k_list = k_list;
+  kp.a_rows = a_rows;
   kp.metric = metric;
   kp.num_ranges = ranges;
   kp.tiles_total = tiles_total;
   kp.gthr = reinterpret_cast<uint32_t*>(ws + cand_bytes + ls_bytes + li_bytes);
+  kp.qscale_out = reinterpret_cast<float*>(ws + cand_bytes + ls_bytes + li_bytes + gt_bytes);
   static const int cross_off = getenv("RS_DENSE_NO_CROSS_THR") ? 1 : 0;  // A/B switch for scripts/batch_bench.py
-  const int gm = (k + ranges - 1) / ranges;
+  const int gm = std::max((k + ranges - 1) / ranges, (k + kDtMaxGroups - 1) / kDtMaxGroups);
   kp.gm = (ranges > 1 && gm <= kDtMaxGm && !cross_off) ? gm : 0;
+  static const int bootstrap_off = getenv("RS_DENSE_NO_BOOTSTRAP") ? 1 : 0;
+  kp.bootstrap = bootstrap_off ? 0 : 1;
+  kp.cross_groups = kp.gm > 0 ? std::min(ranges, (k + kp.gm - 1) / kp.gm) : 1;
   if (kp.gm > 0) {
     cudaError_t me = cudaMemsetAsync(kp.gthr, 0, gt_bytes, stream);
     if (me != cudaSuccess) {
@@ -625,12 +810,14 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
     };
     fprintf(stderr,
             "[dense_tc5 trace] pair %d ranges %d groups %d tiles/range %d | MMA (leader): total %.0f wait full %.0f acc_empty %.0f | "
-            "epilogue warp 4 (leader/peer): total %.0f/%.0f wait acc_full %.0f/%.0f compaction %.0f/%.0f | producer (leader/peer): "
-            "total %.0f/%.0f wait empty %.0f/%.0f  [cycles, mean over CTAs]\n",
+            "epilogue warp 4 (leader/peer): total %.0f/%.0f wait acc_full %.0f/%.0f compaction %.0f/%.0f first-tile bisection %.0f refresh %.0f append path %.0f in %.0f chunks | producer (leader/peer): "
+            "total %.0f/%.0f wait empty %.0f/%.0f  [cycles, mean over CTAs] | whole kernel %.0f cycles in %.0f ns\n",
             (int)pair, ranges, mgroups, tiles_total / ranges, avg(0, 0), avg(1, 0), avg(2, 0), avg(4, 0), avg(4, 1), avg(5, 0),
-            avg(5, 1), avg(6, 0), avg(6, 1), avg(11, 0), avg(11, 1), avg(10, 0), avg(10, 1));
+            avg(5, 1), avg(6, 0), avg(6, 1), avg(7, 0), avg(8, 0), avg(9, 0), avg(12, 0), avg(11, 0), avg(11, 1), avg(10, 0), avg(10, 1), avg(13, -1), avg(14, -1));
   }
-  e = launch_topk_merge(kp.list_scores, kp.list_ids, ranges, nq, k, k, 0, 0, out_scores, out_ids, stream);
+  // the lists are in no particular order; the kernel's final cross-range words bound the answer for the merge
+  e = launch_topk_merge(kp.list_scores, kp.list_ids, ranges, nq, k_list, k, 0, 0, out_scores, out_ids, stream,
+                        kp.gm > 0 ? kp.gthr : nullptr, kp.cross_groups, kp.qscale_out);
   if (e != cudaSuccess) {
     *err = cudaGetErrorString(e);
     return -3;

@@ -45,7 +45,8 @@ cudaError_t launch_dense_scan(ScanParams p, int dtype, int num_sms, bool pdl, cu
 // ------------------------------------------------------------------ top-k list merge
 cudaError_t launch_topk_merge(const float* scores, const int64_t* ids, int nlists, int nq, int k_in, int k_out,
                               int64_t score_list_stride, int64_t id_list_stride, float* out_scores, int64_t* out_ids,
-                              cudaStream_t stream);
+                              cudaStream_t stream, const uint32_t* bound = nullptr, int bound_groups = 0,
+                              const float* bound_scale = nullptr);
 
 // ------------------------------------------------------------------ MaxSim
 struct MaxSimParams {

@@ -30,15 +30,26 @@ namespace rs {
 __global__ void __launch_bounds__(kMergeThreads) topk_merge_kernel(const float* scores, const int64_t* ids, int nlists,
                                                                    int nq, int k_in, int k_out, int cap, int prune,
                                                                    int64_t sstride, int64_t istride, float* out_scores,
-                                                                   int64_t* out_ids) {
+                                                                   int64_t* out_ids, const uint32_t* bound,
+                                                                   int bound_groups, const float* bound_scale) {
   extern __shared__ __align__(16) uint8_t smem[];
+  // bound: [bound_groups, nq] orderable scores, each standing for enough rows that the minimum over the groups has
+  // k_out candidates at or above it (dense_tc5.cu's cross-range words); any zero word = no bound.  The list scores
+  // are those scores times bound_scale[q] (>= 0; the same float product the lists were written with, so the order of
+  // a score and the bound survives the rounding).
+  uint32_t hint = 0u;
+  if (bound) {
+    hint = 0xFFFFFFFFu;
+    for (int g = 0; g < bound_groups; ++g) hint = min(hint, __ldcg(bound + (size_t)g * nq + blockIdx.x));
+    if (hint != 0u && bound_scale) hint = f32_orderable(orderable_f32(hint) * __ldcg(bound_scale + blockIdx.x));
+  }
   merge_one_query(reinterpret_cast<uint64_t*>(smem), scores, ids, nlists, k_in, k_out, cap, prune, sstride, istride,
-                  out_scores, out_ids, (int)blockIdx.x);
+                  out_scores, out_ids, (int)blockIdx.x, hint);
 }
 
 cudaError_t launch_topk_merge(const float* scores, const int64_t* ids, int nlists, int nq, int k_in, int k_out,
                               int64_t score_list_stride, int64_t id_list_stride, float* out_scores, int64_t* out_ids,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, const uint32_t* bound, int bound_groups, const float* bound_scale) {
   if (score_list_stride == 0) score_list_stride = (int64_t)nq * k_in;
   if (id_list_stride == 0) id_list_stride = (int64_t)nq * k_in;
   int cap, prune;
@@ -47,7 +58,8 @@ cudaError_t launch_topk_merge(const float* scores, const int64_t* ids, int nlist
   cudaError_t e = cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   topk_merge_kernel<<<nq, kMergeThreads, smem, stream>>>(scores, ids, nlists, nq, k_in, k_out, cap, prune,
-                                                         score_list_stride, id_list_stride, out_scores, out_ids);
+                                                         score_list_stride, id_list_stride, out_scores, out_ids,
+                                                         bound, bound_groups, bound_scale);
   return cudaGetLastError();
 }
 

@@ -23,12 +23,13 @@ inline void merge_plan(int nlists, int k_in, int k_out, int* cap_out, int* prune
   *prune_out = (cap >= 2048 && nlists >= 2 && nlists <= 2048 && r <= k_in) ? 1 : 0;
 }
 
+// t0_hint: orderable score known to have >= k_out candidates at or above it, or 0.
 // scores / ids: list l of query q at scores + l * sstride + q * k_in (ids alike with istride); entries with id < 0 are
 // padding.  Output [k_out] at out_* + q * k_out in (score desc, id asc) order, padded with (-inf, -1).
 // All kMergeThreads threads of the CTA call this; `keys` is shared memory for `cap` u64 keys.
 __device__ __forceinline__ void merge_one_query(uint64_t* keys, const float* scores, const int64_t* ids, int nlists, int k_in,
                                                 int k_out, int cap, int prune, int64_t sstride, int64_t istride,
-                                                float* out_scores, int64_t* out_ids, int q) {
+                                                float* out_scores, int64_t* out_ids, int q, uint32_t t0_hint = 0u) {
   __shared__ int s_cnt;
   __shared__ uint32_t s_t0;
   const int tid = threadIdx.x;
@@ -45,8 +46,11 @@ __device__ __forceinline__ void merge_one_query(uint64_t* keys, const float* sco
   };
 
   named_bar_sync(kMergeBar, kMergeThreads);  // the previous query of this CTA (persistent callers) is done with keys[]
-  uint32_t t0 = 0;  // orderable score below which a candidate cannot be in the answer (0 = keep everything)
-  if (prune) {
+  // orderable score below which a candidate cannot be in the answer (0 = keep everything).  A caller that already
+  // knows such a bound passes it as t0_hint (the batched dense kernel: its cross-range threshold; its lists are in no
+  // particular order, which the bound computed below does not exploit well).
+  uint32_t t0 = t0_hint;
+  if (prune && t0_hint == 0u) {
     const int r = (k_out + nlists - 1) / nlists;  // <= k_in
     const int need = (k_out + r - 1) / r;         // lists whose r-th entries bound the answer (<= nlists)
     int n2 = 64;

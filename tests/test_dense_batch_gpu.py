@@ -208,3 +208,31 @@ def test_batched_with_a_filter_per_query(engine, nq):
     assert (i[1, 3:] == -1).all()
     engine.dense_topk(c.to(engine.device), q.to(engine.device), k, mask=masks)
     assert engine.last_dense_impl == _ffi.RS_DENSE_TCGEN05
+
+
+@pytest.mark.parametrize("scale", [1e17, 1e-17])
+def test_batched_first_tile_threshold_extreme_magnitudes(engine, scale):
+    """The first tile's threshold is bisected between its lowest and highest score: inner products near the ends
+    of the fp32 range must neither overflow the midpoint nor lose rows."""
+    n, d, nq, k = 4096, 128, 16, 10
+    c, q = _case(91, n, d, nq, torch.bfloat16, normalise=False)
+    c = (c.float() * scale).to(torch.bfloat16)
+    q = (q.float() * scale).to(torch.bfloat16)
+    s, i = _run(engine, c, q, k, _ffi.RS_DENSE_TCGEN05, metric=_ffi.RS_METRIC_IP)
+    _check_all(s, i, c, q, k, metric=_ffi.RS_METRIC_IP)
+
+
+@pytest.mark.parametrize("passing_in_first_tile", [0, 9, 10, 11])
+def test_batched_first_tile_threshold_with_sparse_filter(engine, passing_in_first_tile):
+    """k = 10 with 0 / k-1 / k / k+1 admissible rows in each range's first tile: the bisected threshold may only be
+    used when the tile holds at least k admissible rows."""
+    n, d, nq, k = 148 * 256 * 3, 64, 8, 10
+    c, q = _case(92, n, d, nq, torch.bfloat16)
+    bits = np.zeros(n, bool)
+    g = np.random.default_rng(5)
+    for t in range(n // 256):
+        m = passing_in_first_tile if t < 148 else 40
+        bits[t * 256 + g.choice(256, m, replace=False)] = True
+    mask = torch.from_numpy(odense.pack_mask(bits).view(np.int32).copy()).to(engine.device)
+    s, i = _run(engine, c, q, k, _ffi.RS_DENSE_TCGEN05, mask=mask)
+    _check_all(s, i, c, q, k, bits)
