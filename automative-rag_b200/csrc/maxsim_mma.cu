@@ -326,16 +326,22 @@ cudaError_t launch_maxsim_mma(const MaxSimParams& p, int dtype, int num_sms, cud
 
 // ================================================================================= fp32 SIMT
 // Exact fp32 FMA path for RS_F32 inputs (the reference's CPU dtype; deployed sizes are tiny:
-// <= 40 docs x 256 tokens, rerankers.py:32-33, mode_config.py).  One CTA per (query, doc);
-// a warp owns doc tokens warp, warp+4, ...; lanes split d; the query lives in shared memory.
+// <= 40 docs x 256 tokens, rerankers.py:32-33, mode_config.py).  One CTA per (query, doc).
+// A lane owns ONE query token (blocks of 32 when lq > 32) and a warp 8 document tokens at a time: the query sits
+// transposed in shared memory (Qt[e][i]: the lanes read consecutive words), a document token's values arrive as
+// float4 loads of one address for the whole warp (a broadcast), every product is an fp32 FMA in ascending e, and the
+// running (max, arg max) of a query token stays in its lane's registers — no shuffles, 32 FMAs per 12 loads.
+// (Round 1 split d over the lanes and butterfly-reduced every (query token, doc token) pair: 475 us for BASELINE
+// config 1, where the arithmetic is 74 MFMA.)
 constexpr int kSimtThreads = 128;
+constexpr int kSimtTokens = 8;
 
 __global__ void __launch_bounds__(kSimtThreads) maxsim_simt_kernel(const MaxSimParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int d = p.d, lq = p.lq;
-  float* Qs = reinterpret_cast<float*>(smem);         // [lq][d]
-  float* red_v = Qs + (size_t)lq * d;                 // [4][lq]
-  int* red_i = reinterpret_cast<int*>(red_v + 4 * lq);  // [4][lq]
+  const int d = p.d, lq = p.lq, lqp = (lq + 31) & ~31;
+  float* Qt = reinterpret_cast<float*>(smem);           // [d][lqp]
+  float* red_v = Qt + (size_t)lqp * d;                  // [4][lqp]
+  int* red_i = reinterpret_cast<int*>(red_v + 4 * lqp);  // [4][lqp]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qi = blockIdx.y, slot = blockIdx.x;
   const int ndo = p.cand ? p.nc : p.nd;
@@ -343,24 +349,46 @@ __global__ void __launch_bounds__(kSimtThreads) maxsim_simt_kernel(const MaxSimP
   const bool in_range = dc >= 0 && dc < p.nd;  // outside the collection: an empty document, score -inf
   const int beg = in_range ? p.doc_offsets[dc] : 0, len = in_range ? max(p.doc_offsets[dc + 1] - beg, 0) : 0;
   const float* qg = reinterpret_cast<const float*>(p.q) + (size_t)qi * lq * d;
-  for (int i = tid; i < lq * d; i += kSimtThreads) Qs[i] = qg[i];
-  for (int i = tid; i < 4 * lq; i += kSimtThreads) {
-    red_v[i] = -CUDART_INF_F;
-    red_i[i] = 0;
+  for (int x = tid; x < lqp * d; x += kSimtThreads) {
+    const int i = x / d, e = x - i * d;  // coalesced read of Q[i][e]
+    Qt[(size_t)e * lqp + i] = i < lq ? qg[x] : 0.f;
   }
   __syncthreads();
   const float* dg = reinterpret_cast<const float*>(p.doc_tokens) + (size_t)beg * d;
-  for (int j = warp; j < len; j += 4) {
-    const float* row = dg + (size_t)j * d;
-    for (int i = 0; i < lq; ++i) {
-      float acc = 0.f;
-      for (int e = lane; e < d; e += 32) acc = fmaf(Qs[(size_t)i * d + e], __ldg(row + e), acc);
-      acc = warp_sum(acc);
-      if (lane == 0 && acc > red_v[warp * lq + i]) {  // rows visited in increasing j: first max kept
-        red_v[warp * lq + i] = acc;
-        red_i[warp * lq + i] = j;
+  for (int ib = 0; ib < lqp; ib += 32) {
+    float best = -CUDART_INF_F;
+    int best_j = 0;
+    const float* qcol = Qt + ib + lane;
+    for (int j0 = warp * kSimtTokens; j0 < len; j0 += 4 * kSimtTokens) {
+      float acc[kSimtTokens];
+      const float4* rows[kSimtTokens];
+#pragma unroll
+      for (int t = 0; t < kSimtTokens; ++t) {
+        acc[t] = 0.f;
+        rows[t] = reinterpret_cast<const float4*>(dg + (size_t)min(j0 + t, len - 1) * d);  // past the end: a repeat
+      }
+      for (int e = 0; e < d; e += 4) {
+        const float q0 = qcol[(size_t)e * lqp], q1 = qcol[(size_t)(e + 1) * lqp];
+        const float q2 = qcol[(size_t)(e + 2) * lqp], q3 = qcol[(size_t)(e + 3) * lqp];
+#pragma unroll
+        for (int t = 0; t < kSimtTokens; ++t) {
+          const float4 v = __ldg(rows[t] + (e >> 2));
+          acc[t] = fmaf(q0, v.x, acc[t]);
+          acc[t] = fmaf(q1, v.y, acc[t]);
+          acc[t] = fmaf(q2, v.z, acc[t]);
+          acc[t] = fmaf(q3, v.w, acc[t]);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < kSimtTokens; ++t) {
+        if (j0 + t < len && acc[t] > best) {  // tokens visited in increasing j: the first maximum is kept
+          best = acc[t];
+          best_j = j0 + t;
+        }
       }
     }
+    red_v[warp * lqp + ib + lane] = best;
+    red_i[warp * lqp + ib + lane] = best_j;
   }
   __syncthreads();
   if (warp == 0) {
@@ -369,8 +397,8 @@ __global__ void __launch_bounds__(kSimtThreads) maxsim_simt_kernel(const MaxSimP
       float v = red_v[i];
       int ix = red_i[i];
       for (int w = 1; w < 4; ++w) {
-        float ov = red_v[w * lq + i];
-        int oi = red_i[w * lq + i];
+        float ov = red_v[w * lqp + i];
+        int oi = red_i[w * lqp + i];
         if (ov > v || (ov == v && oi < ix)) {
           v = ov;
           ix = oi;
@@ -387,7 +415,10 @@ __global__ void __launch_bounds__(kSimtThreads) maxsim_simt_kernel(const MaxSimP
   }
 }
 
-size_t maxsim_simt_smem_bytes(int lq, int d) { return (size_t)lq * d * 4 + (size_t)8 * lq * 4; }
+size_t maxsim_simt_smem_bytes(int lq, int d) {
+  const size_t lqp = (size_t)((lq + 31) & ~31);
+  return lqp * d * 4 + (size_t)8 * lqp * 4;
+}
 
 cudaError_t launch_maxsim_simt(const MaxSimParams& p, cudaStream_t stream) {
   const int ndo = p.cand ? p.nc : p.nd;

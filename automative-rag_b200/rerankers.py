@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import logging
 import time
+from operator import attrgetter
 from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -24,6 +25,8 @@ from . import _ffi
 from .documents import Document
 
 logger = logging.getLogger(__name__)
+_shape_of = attrgetter("shape")
+_dtype_of = attrgetter("dtype")
 
 
 # Pinned staging for host-resident embeddings (the reference's CPU call shape): the rows are concatenated straight
@@ -171,21 +174,29 @@ class B200ColBERTReranker:
         (mixed devices / dtypes, [1, Ld, D] entries, views) takes the general pack-and-call path."""
         q2 = q[0] if q.dim() == 3 else q
         dev = self.engine.device
-        d0 = docs[0]
         if q2.dim() != 2 or not q2.is_contiguous() or q2.dtype not in (torch.float16, torch.bfloat16, torch.float32):
             return None
-        if q2.device.type != "cpu" and q2.device != dev:
+        if q2.is_cuda and q2.device != dev:
             return None
-        for t in docs:
-            if t.dim() != 2 or t.dtype != q2.dtype or t.device != d0.device or not t.is_contiguous() or t.shape[1] != q2.shape[1]:
-                return None
-            if t.shape[0] == 0:
-                raise ValueError("document with zero tokens")  # torch.max over an empty dim raises in the reference too
-        if d0.device.type != "cpu" and d0.device != dev:
+        d = q2.shape[1]
+        if d % 8:
             return None
-        if q2.shape[1] % 8:
+        # one C-level pass per property (map / set / all) instead of a Python loop over the documents: this check is
+        # on the latency path of every rerank call
+        try:
+            lens = [n for n, dd in map(_shape_of, docs) if dd == d]
+        except ValueError:  # an entry that is not 2-D
             return None
-        return self.engine.maxsim_list(q2, docs, self.compute_dtype)
+        if len(lens) != len(docs):
+            return None
+        if set(map(_dtype_of, docs)) != {q2.dtype} or not all(map(torch.Tensor.is_contiguous, docs)):
+            return None
+        where = set(map(torch.Tensor.get_device, docs))  # -1 = host
+        if len(where) != 1 or (where != {-1} and where != {dev.index}):
+            return None
+        if 0 in lens:
+            raise ValueError("document with zero tokens")  # torch.max over an empty dim raises in the reference too
+        return self.engine.maxsim_list(q2, docs, self.compute_dtype, doc_lens=lens)
 
     # -- rerank tail --------------------------------------------------------------------------
     def _order(self, scores: torch.Tensor, other: Optional[torch.Tensor], top_k: Optional[int]
