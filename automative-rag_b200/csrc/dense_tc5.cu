@@ -664,13 +664,17 @@ __global__ void __launch_bounds__(kDtThreads, 1)
 
 // ================================================================================ host side
 bool tc5_dense_supported(const Tc5State* s, int64_t n, int d, int nq, int k, const uint32_t* mask,
-                         int64_t mask_stride_words) {
+                         int64_t mask_stride_words, bool worthwhile) {
   (void)mask;
   if (!s) return false;
-  // One batched pass over the corpus beats a loop of single-query scans from 4 queries on (1M x 1024 rows, k = 10:
-  // 0.60 vs 1.15 ms at 4 queries, 1.1 vs 9.2 ms at 32; profiles/r01_batch_crossover.txt).
-  static const int min_nq = getenv("RS_DENSE_TC_MIN_NQ") ? atoi(getenv("RS_DENSE_TC_MIN_NQ")) : 4;
-  if (nq < min_nq || n < kDtBN) return false;
+  // One batched pass over the corpus beats a loop of single-query scans from 4 queries on at every corpus size, and
+  // from 2 queries once the corpus is large enough for the pass to be HBM-bound (1M x 1024 rows, k = 10: 0.35 ms for
+  // 2..32 queries vs 0.59 ms for two scans; 20k rows: 0.053 vs 0.038 ms; profiles/r02_batch_crossover.txt).
+  static const int min_nq = getenv("RS_DENSE_TC_MIN_NQ") ? atoi(getenv("RS_DENSE_TC_MIN_NQ")) : 0;
+  if (n < kDtBN) return false;
+  if (nq < 2) return false;
+  // `worthwhile` (the AUTO choice) adds the profitability rule to what the kernel can do
+  if (worthwhile && (min_nq > 0 ? nq < min_nq : (nq < 4 && n < 200000))) return false;
   if (d % kDtBK != 0 || d < kDtBK) return false;
   if (k > 128) return false;
   (void)mask_stride_words;                       // a filter per query is a per-thread mask word in the epilogue

@@ -319,10 +319,11 @@ int rs_dense_topk(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_
   const int64_t scan_bytes = n * (int64_t)d * 2;
 
   int impl = h->dense_impl;
-  if (impl == RS_DENSE_AUTO) impl = rs::tc5_dense_supported(h->tc5, n, d, nq, k, mask, mask_stride_words) ? RS_DENSE_TCGEN05 : RS_DENSE_SCAN;
+  if (impl == RS_DENSE_AUTO)
+    impl = rs::tc5_dense_supported(h->tc5, n, d, nq, k, mask, mask_stride_words, /*worthwhile=*/true) ? RS_DENSE_TCGEN05 : RS_DENSE_SCAN;
   if (impl == RS_DENSE_TCGEN05) {
     if (!rs::tc5_dense_supported(h->tc5, n, d, nq, k, mask, mask_stride_words))
-      return fail(h, RS_ERR_UNSUPPORTED, "rs_dense_topk: tcgen05 batched path needs nq >= 4, n >= 256, d %% 64 == 0, k <= 128");
+      return fail(h, RS_ERR_UNSUPPORTED, "rs_dense_topk: tcgen05 batched path needs nq >= 2, n >= 256, d %% 64 == 0, k <= 128");
     int launched = 0;
     std::string err;
     int rc = rs::tc5_dense_topk(h->tc5, corpus, n, d, dtype, inv_norm, metric, queries, nq, mask, mask_stride_words, k, id_base, out_scores,

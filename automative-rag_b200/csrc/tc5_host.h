@@ -33,7 +33,7 @@ bool tc5_encode(const Tc5State* s, CUtensorMap* map, int dtype, int rank, const 
 
 // Batched dense top-k (GEMM + fused per-row top-k).
 bool tc5_dense_supported(const Tc5State* s, int64_t n, int d, int nq, int k, const uint32_t* mask,
-                         int64_t mask_stride_words);
+                         int64_t mask_stride_words, bool worthwhile = false);
 int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype, const float* inv_norm, int metric,
                    const void* queries, int nq, const uint32_t* mask, int64_t mask_stride_words, int k, int64_t id_base, float* out_scores,
                    int64_t* out_ids, cudaStream_t stream, int* launched, std::string* err);

@@ -145,9 +145,15 @@ def test_batched_agrees_with_scan_and_auto_dispatch(engine):
     engine.dense_topk(c.to(engine.device), q[:4].to(engine.device), k)
     assert engine.last_dense_impl == _ffi.RS_DENSE_TCGEN05    # ... from four queries on (one pass over the corpus)
     engine.dense_topk(c.to(engine.device), q[:3].to(engine.device), k)
-    assert engine.last_dense_impl == _ffi.RS_DENSE_SCAN       # fewer: a loop of HBM-bound scans
+    assert engine.last_dense_impl == _ffi.RS_DENSE_SCAN       # fewer over a small corpus: a loop of scans
     engine.dense_topk(c.to(engine.device), q[:1].to(engine.device), k)
     assert engine.last_dense_impl == _ffi.RS_DENSE_SCAN       # a single query to the HBM-bound scan
+    big = torch.zeros(200_000, 64, dtype=torch.bfloat16, device=engine.device)
+    big[:, 0] = 1
+    q2 = torch.ones(2, 64, dtype=torch.bfloat16, device=engine.device)
+    s2, i2 = engine.dense_topk(big, q2, 3)
+    assert engine.last_dense_impl == _ffi.RS_DENSE_TCGEN05    # two queries over a large corpus: one pass again
+    assert i2.cpu().tolist() == [[0, 1, 2], [0, 1, 2]]        # all rows tie: the lowest ids
 
 
 def test_config3_reduced_rows_properties(engine):
