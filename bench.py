@@ -564,6 +564,22 @@ def extra_single_gpu(cx, corpus, queries):
         ms = timed(lambda: eng.dense_topk(corpus, queries[:1], kk), 30)
         out[f"dense_k{kk}"] = {"ms_per_query": ms, "queries_per_s": 1e3 / ms}
 
+    # small batches over the headline corpus: ONE pass of the tcgen05 kernel for the whole batch (AUTO dispatch), its
+    # roof the corpus bytes at the HBM peak (the scan loop costs one such pass PER QUERY)
+    try:
+        eng.set_dense_impl(_ffi.RS_DENSE_AUTO)
+        for nq_b in (2, 8, 32, 128):
+            qb = queries[:nq_b] if queries.shape[0] >= nq_b else queries.repeat((nq_b + queries.shape[0] - 1) // queries.shape[0], 1)[:nq_b]
+            ms = timed(lambda: eng.dense_topk(corpus, qb, TOPK), 30)
+            assert eng.last_dense_impl == _ffi.RS_DENSE_TCGEN05, "AUTO did not pick the batched kernel"
+            alg = n * DIM * 2
+            out[f"dense_batch_{nq_b}q"] = {"ms_per_batch": ms, "queries_per_s": nq_b / ms * 1e3, "k": TOPK,
+                                           "achieved_gbs": alg / ms / 1e6, "frac_of_hbm": alg / ms / 1e6 / hbm_peak}
+    except Exception as e:  # noqa: BLE001
+        out["dense_batch_small"] = {"error": str(e)}
+    finally:
+        eng.set_dense_impl(_ffi.RS_DENSE_SCAN)
+
     # BASELINE config 3: 1024 queries x 10M x 1024 bf16, top-100 — tcgen05 GEMM + fused per-query top-k
     try:
         torch.cuda.empty_cache()
@@ -584,6 +600,8 @@ def extra_single_gpu(cx, corpus, queries):
             "roofline": {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": cx.tf_sustained, "unit": "TFLOP/s",
                          "frac": fl / ms / 1e9 / cx.tf_sustained, "traffic": None,
                          "peak_source": "measured sustained" if "bf16_tflops_sustained" in peaks else "fallback"}}
+        if not cx.args.no_parity:
+            out["dense_batch_config3"].update(parity_config3(eng, c3, q3, k3))
         del c3
         torch.cuda.empty_cache()
     except Exception as e:  # noqa: BLE001
@@ -735,6 +753,69 @@ def extra_config4_sharded(cx):
         "parity": {"sharded_equals_unsharded_bitwise": cx.all_ok(same_b), "max_rel_err_vs_cpu_oracle_2_queries": err_b,
                    "ok": cx.all_ok(same_b and err_b < 1e-3)}}
     return out
+
+
+def parity_config3(eng, c3, q3, k3, n_check=2):
+    """SURVEY §8d protocol for the batched kernel at config 3's FULL size (10M rows), `n_check` of the 1024 queries,
+    CPU side in numpy fp32 on the bf16-rounded values: (i) every returned score recomputed from its row; (ii) no row
+    out of 1M sampled non-returned rows beats the k-th returned score beyond tolerance; (iii) the kernel's top-k over
+    the first 1M rows (all 1024 queries in the launch) against the full CPU oracle of that slice, tie-aware."""
+    import time
+
+    import numpy as np
+    import torch
+
+    from tests._parity import assert_scores_close, assert_topk_matches
+
+    t0 = time.perf_counter()
+    dev = c3.device
+    n3 = c3.shape[0]
+    detail, ok = {}, True
+    try:
+        s, i = eng.dense_topk(c3, q3, k3)
+        torch.cuda.synchronize()
+        which = [0, q3.shape[0] - 1][:n_check]
+        qf = q3[which].float().cpu().numpy()
+        qf = qf / np.linalg.norm(qf, axis=1, keepdims=True)  # the kernel scales by 1/|q| (cosine, unit corpus rows)
+
+        def scores_of(rows_dev):  # [m, d] bf16 on the device -> fp32 scores [m, n_check] on the CPU, chunked
+            outv = np.empty((rows_dev.shape[0], len(which)), dtype=np.float32)
+            for a in range(0, rows_dev.shape[0], 262144):
+                outv[a: a + 262144] = rows_dev[a: a + 262144].float().cpu().numpy() @ qf.T
+            return outv
+
+        worst = 0.0
+        for j, qi in enumerate(which):
+            ids, got = i[qi], s[qi].cpu().numpy()
+            want = scores_of(c3[ids])[:, j]
+            assert_scores_close(got, want, what="config3 (i) returned scores")
+            worst = max(worst, float(np.abs(got - want).max()))
+        detail["i_returned_scores_max_abs_err"] = worst
+        nblk, blk_rows = 1024, 1024
+        rng = np.random.default_rng(77)
+        starts = np.sort(rng.choice((n3 - blk_rows) // blk_rows, size=nblk, replace=False)) * blk_rows
+        idx = (torch.from_numpy(starts).to(dev)[:, None] + torch.arange(blk_rows, device=dev)[None, :]).reshape(-1)
+        sc = scores_of(c3[idx])
+        beat = 0
+        for j, qi in enumerate(which):
+            ids, got = i[qi].cpu().numpy(), s[qi].cpu().numpy()
+            kth = float(got.min())
+            rest = sc[~np.isin(idx.cpu().numpy(), ids), j]
+            beat += int((rest > kth + 1e-3 * max(abs(kth), float(np.abs(rest).max())) + 1e-6).sum())
+        detail["ii_threshold_sampled_rows"] = int(idx.numel())
+        detail["ii_rows_beating_kth"] = beat
+        ok &= beat == 0
+        n_slice = min(1_000_000, n3)
+        s_sl, i_sl = eng.dense_topk(c3[:n_slice], q3, k3)
+        all_sc = scores_of(c3[:n_slice])
+        for j, qi in enumerate(which):
+            assert_topk_matches(s_sl[qi].cpu().numpy(), i_sl[qi].cpu().numpy(), all_sc[:, j], np.ones(n_slice, bool), k3)
+        detail["iii_oracle_slice_rows"] = n_slice
+    except AssertionError as e:
+        ok = False
+        detail["failure"] = str(e)[:300]
+    return {"parity": bool(ok), "parity_detail": {**detail, "queries_checked": n_check, "seconds": round(time.perf_counter() - t0, 1),
+                                                  "protocol": "SURVEY §8d (i)-(iii) at 10M rows; CPU numpy fp32"}}
 
 
 # ------------------------------------------------------------------------------------------ every N: config 5
