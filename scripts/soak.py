@@ -22,6 +22,9 @@ while time.time() - t0 < budget:
     nq = int(rng.choice([1, 1, 3, 5, 40, 64, 200]))
     c = big[dt][:n, :d].contiguous()
     q = torch.randn(nq, d, generator=g, device=dev).to(dt)
+    if rng.random() < 0.15:   # coarse values: thousands of exactly tied scores (first-tile bisection / list cut fall-backs)
+        c = (c.float() * 0.7).round().to(dt)
+        q = q.float().round().to(dt)
     p = float(rng.choice([1.0, 1.0, 0.9, 0.5, 0.05, 0.0]))
     bits = None if p == 1.0 else (rng.random(n) < p)
     mask = None if bits is None else torch.from_numpy(pack_bits(bits)).to(dev)
