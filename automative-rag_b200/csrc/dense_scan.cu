@@ -31,7 +31,10 @@
 //     round of END markers, so all consumer warps leave the loop in the same round.
 //   * every CTA writes its sorted top-k to the workspace; the last CTA to finish (atomic
 //     ticket) merges the grid's lists and writes the final (score, id) pairs — no second launch.
+#include <cuda.h>
+
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -64,6 +67,19 @@ __device__ __forceinline__ uint64_t policy_evict_normal_() {
   return pol;
 }
 
+// TMA tile::gather4: FOUR arbitrary rows of a 2-D tensor in one instruction.  The corpus is described to TMA as
+// [n][row_bytes / 8] 8-byte elements (box = one whole row, <= 256 elements = 2 KB), so one gather4 moves four
+// passing rows = a whole 8 KB gather tile at d = 1024 — a quarter of the bulk-copy instructions of the
+// copy-per-row path, whose per-instruction cost is what holds sparse filters below the HBM rate.
+__device__ __forceinline__ void tma_gather4(void* dst_smem, const CUtensorMap* map, uint32_t r0, uint32_t r1, uint32_t r2,
+                                            uint32_t r3, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;" ::"r"(smem_u32(dst_smem)),
+      "l"(map), "r"(smem_u32(bar)), "r"(0), "r"((int)r0), "r"((int)r1), "r"((int)r2), "r"((int)r3), "l"(policy)
+      : "memory");
+}
+
 // diagnostics: thread 0 stamps phase i of its CTA when a trace buffer is attached (rs_set_scan_trace)
 __device__ __forceinline__ void scan_trace(const ScanParams& p, int i) {
   if (p.trace != nullptr && threadIdx.x == 0) {
@@ -74,7 +90,8 @@ __device__ __forceinline__ void scan_trace(const ScanParams& p, int i) {
 }
 
 template <typename T, int NCH>
-__global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(kScanThreads, 1)
+    dense_scan_kernel(const ScanParams p, const __grid_constant__ CUtensorMap gmap) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tile_rows = p.tile_rows;
   const int S = p.stages;
@@ -197,7 +214,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
     };
     // Gather tiles: lane (t, j) = (lane / tile_rows, lane % tile_rows) copies queued row
     // head + t*nr + j into row j of tile t's slot — one bulk copy per RUN of consecutive rows.
+    // With a row tensor map (p.gather4) a full tile goes out as one gather4 per four rows.
     const int lanes_per_tile_shift = 31 - __clz(tile_rows);
+    const bool g4 = p.gather4 != 0;
     auto issue_gather = [&](int ntiles, int nr) {
       const int t = lane >> lanes_per_tile_shift, j = lane & (tile_rows - 1);
       const bool in = t < ntiles && j < nr;
@@ -216,7 +235,14 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
         mbar_arrive_expect_tx(&full_bar[stage], row_bytes * nr);
       }
       __syncwarp();
-      if (in && start) {
+      const uint32_t r1 = __shfl_down_sync(0xFFFFFFFFu, row, 1);
+      const uint32_t r2 = __shfl_down_sync(0xFFFFFFFFu, row, 2);
+      const uint32_t r3 = __shfl_down_sync(0xFFFFFFFFu, row, 3);
+      if (g4 && nr == tile_rows) {
+        if (in && (j & 3) == 0)
+          tma_gather4(stage_base + (size_t)stage * tile_bytes + (size_t)j * row_bytes, &gmap, row, r1, r2, r3,
+                      &full_bar[stage], pol);
+      } else if (in && start) {
         const uint32_t later = lane == 31 ? 0u : (starts >> (lane + 1));
         const int run = later ? __ffs(later) : (32 - lane);
         bulk_g2s(stage_base + (size_t)stage * tile_bytes + (size_t)j * row_bytes, corpus + (size_t)row * row_bytes,
@@ -526,7 +552,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) dense_scan_kernel(const ScanP
 }
 
 template <typename T>
-static cudaError_t launch_scan_t(const ScanParams& p, int grid, size_t smem, bool pdl, cudaStream_t stream) {
+static cudaError_t launch_scan_t(const ScanParams& p, const CUtensorMap& gmap, int grid, size_t smem, bool pdl,
+                                 cudaStream_t stream) {
   const int nch = (p.d + 255) / 256;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
@@ -543,7 +570,7 @@ static cudaError_t launch_scan_t(const ScanParams& p, int grid, size_t smem, boo
     cudaError_t e = cudaFuncSetAttribute(dense_scan_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)smem);                                                         \
     if (e != cudaSuccess) return e;                                                                          \
-    return cudaLaunchKernelEx(&cfg, dense_scan_kernel<T, N>, p);                                             \
+    return cudaLaunchKernelEx(&cfg, dense_scan_kernel<T, N>, p, gmap);                                            \
   }
   if (nch <= 1) RS_SCAN_CASE(1)
   if (nch <= 2) RS_SCAN_CASE(2)
@@ -630,8 +657,22 @@ static int scan_unit_words(int d) {
   return lo > 32 ? 32 : (int)lo;
 }
 
-cudaError_t launch_dense_scan(ScanParams p, int dtype, int num_sms, bool pdl, cudaStream_t stream) {
+bool scan_gather4_supported(int d) {
+  // one box = one whole row of <= 256 8-byte elements; a gather4 lands four rows = a multiple of 128 bytes
+  return d % 16 == 0 && d <= 1024 && scan_tile_rows(d) >= 4;
+}
+
+cudaError_t launch_dense_scan(ScanParams p, int dtype, int num_sms, bool pdl, cudaStream_t stream,
+                              const CUtensorMap* gather_map) {
   const ScanPlan pl = scan_plan(p.d, p.k);
+  alignas(64) CUtensorMap gmap;
+  if (gather_map != nullptr && p.mask != nullptr && scan_gather4_supported(p.d)) {
+    gmap = *gather_map;
+    p.gather4 = 1;
+  } else {
+    memset(&gmap, 0, sizeof(gmap));
+    p.gather4 = 0;
+  }
   p.tile_rows = pl.tile_rows;
   p.consumers = pl.consumers;
   p.stages = pl.stages;
@@ -651,8 +692,8 @@ cudaError_t launch_dense_scan(ScanParams p, int dtype, int num_sms, bool pdl, cu
   first = first > p.grab_max ? p.grab_max : first;
   p.first_words = first < p.unit_words ? 0 : (int32_t)first;
   const size_t smem = pl.smem;
-  if (dtype == 0) return launch_scan_t<__half>(p, grid, smem, pdl, stream);
-  return launch_scan_t<__nv_bfloat16>(p, grid, smem, pdl, stream);
+  if (dtype == 0) return launch_scan_t<__half>(p, gmap, grid, smem, pdl, stream);
+  return launch_scan_t<__nv_bfloat16>(p, gmap, grid, smem, pdl, stream);
 }
 
 }  // namespace rs

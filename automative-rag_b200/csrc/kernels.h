@@ -1,5 +1,6 @@
 // kernels.h — host-visible launchers of the sm_100a kernels (internal to the library).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -32,6 +33,7 @@ struct ScanParams {
   int32_t grab_max;        // largest grab in mask words (<= 32), filled by the launcher
   int32_t first_words;     // words per CTA handed out statically before the counter is used (0 = none)
   uint64_t* trace;         // diagnostics (rs_set_scan_trace): [grid][8] %globaltimer stamps, or null
+  int32_t gather4;         // filled by the launcher: gather tiles go out as TMA tile::gather4 (row tensor map given)
 };
 int scan_tile_rows(int d);
 size_t scan_smem_bytes(int d, int k);
@@ -40,7 +42,11 @@ size_t scan_smem_bytes(int d, int k);
 void scan_plan_query(int d, int k, int64_t out[7]);
 // pdl: launch with programmatic stream serialization (only between consecutive scans of one call,
 // whose inputs are all complete before the first launch; see dense_scan.cu)
-cudaError_t launch_dense_scan(ScanParams p, int dtype, int num_sms, bool pdl, cudaStream_t stream);
+// gather_map: tensor map of the corpus as [n][2d / 8] 8-byte elements, box = one row (tc5_encode_rows), or null:
+// with a filter mask the passing rows of sparse mask words are then fetched four per TMA instruction.
+bool scan_gather4_supported(int d);
+cudaError_t launch_dense_scan(ScanParams p, int dtype, int num_sms, bool pdl, cudaStream_t stream,
+                              const CUtensorMap* gather_map = nullptr);
 
 // ------------------------------------------------------------------ top-k list merge
 cudaError_t launch_topk_merge(const float* scores, const int64_t* ids, int nlists, int nq, int k_in, int k_out,

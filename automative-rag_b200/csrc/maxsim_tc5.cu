@@ -584,6 +584,32 @@ bool tc5_encode(const Tc5State* s, CUtensorMap* map, int dtype, int rank, const 
   return true;
 }
 
+// The corpus as [n_rows][row_bytes / 8] 8-byte elements, box = one whole row, no swizzle: the map the
+// single-query scan's tile::gather4 copies read (dense_scan.cu), four arbitrary rows per instruction.
+bool tc5_encode_rows(const Tc5State* s, CUtensorMap* map, const void* base, uint64_t n_rows, uint32_t row_bytes,
+                     std::string* err) {
+  if (!s || !s->encode) {
+    if (err) *err = "cuTensorMapEncodeTiled entry point not available";
+    return false;
+  }
+  if (row_bytes % 16 != 0 || row_bytes / 8 > 256 || n_rows == 0) {
+    if (err) *err = "row tensor map: unsupported row size";
+    return false;
+  }
+  cuuint64_t gdim[2] = {row_bytes / 8, n_rows};
+  cuuint64_t gstr[1] = {row_bytes};
+  cuuint32_t bdim[2] = {row_bytes / 8, 1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = s->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = "cuTensorMapEncodeTiled(rows) failed with CUresult " + std::to_string((int)r);
+    return false;
+  }
+  return true;
+}
+
 int tc5_num_sms(const Tc5State* s) { return s->num_sms; }
 bool tc5_has_encode(const Tc5State* s) { return s->encode != nullptr; }
 

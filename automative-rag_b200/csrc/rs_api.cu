@@ -28,6 +28,12 @@ struct rs_handle {
   // on the device.  Calls on ONE stream are ordered by the stream; when the stream changes, the new stream waits for
   // an event recorded on the previous one (order_after_last).
   cudaStream_t last_stream = nullptr;
+  // row tensor map of the last filtered scan's corpus (tile::gather4, dense_scan.cu)
+  alignas(64) CUtensorMap gmap;
+  const void* gmap_corpus = nullptr;
+  int64_t gmap_n = -1;
+  int32_t gmap_d = -1;
+  bool gmap_ok = false;
   bool has_last = false;
   cudaEvent_t order_ev = nullptr;
   // dense scan workspace
@@ -337,6 +343,20 @@ int rs_dense_topk(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_
 
   h->last_dense_impl = RS_DENSE_SCAN;
   const size_t elt = 2;
+  // Filtered scans fetch the passing rows of sparse mask words four per TMA instruction (tile::gather4) through a
+  // row tensor map of the corpus; encoded on the host (~1 us) when the corpus changes, kept in the handle.
+  const CUtensorMap* gather_map = nullptr;
+  static const bool no_gather4 = getenv("RS_SCAN_NO_GATHER4") != nullptr;
+  if (mask != nullptr && n > 0 && !no_gather4 && rs::scan_gather4_supported(d)) {
+    if (h->gmap_corpus != corpus || h->gmap_n != n || h->gmap_d != d) {
+      std::string err;
+      h->gmap_ok = rs::tc5_encode_rows(h->tc5, &h->gmap, corpus, (uint64_t)n, (uint32_t)d * 2u, &err);
+      h->gmap_corpus = corpus;
+      h->gmap_n = n;
+      h->gmap_d = d;
+    }
+    if (h->gmap_ok) gather_map = &h->gmap;
+  }
   for (int qi = 0; qi < nq; ++qi) {
     rs::ScanParams p{};
     p.corpus = corpus;
@@ -356,7 +376,7 @@ int rs_dense_topk(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_
     p.out_ids = out_ids + (size_t)qi * k;
     const int ctr = (int)((h->scan_seq - 1) & (kScanCounters - 1));
     p.unit_counter = h->unit_ctr + ctr;
-    cudaError_t e = rs::launch_dense_scan(p, dtype, h->num_sms, /*pdl=*/qi > 0, st);
+    cudaError_t e = rs::launch_dense_scan(p, dtype, h->num_sms, /*pdl=*/qi > 0, st, gather_map);
     if (e != cudaSuccess) return cuda_fail(h, e, "dense_scan_kernel launch");
     h->launches += 1;
   }

@@ -31,6 +31,9 @@ int tc5_num_sms(const Tc5State* s);
 bool tc5_encode(const Tc5State* s, CUtensorMap* map, int dtype, int rank, const void* base, const uint64_t* dims,
                 const uint64_t* strides_bytes, const uint32_t* box, std::string* err);
 
+bool tc5_encode_rows(const Tc5State* s, CUtensorMap* map, const void* base, uint64_t n_rows, uint32_t row_bytes,
+                     std::string* err);
+
 // Batched dense top-k (GEMM + fused per-row top-k).
 bool tc5_dense_supported(const Tc5State* s, int64_t n, int d, int nq, int k, const uint32_t* mask,
                          int64_t mask_stride_words, bool worthwhile = false);

@@ -145,6 +145,7 @@ def test_sass_of_the_hot_kernels_uses_the_blackwell_units():
 
     for k, sass in kernels("dense_scan_kernel").items():
         assert "UBLKCP" in sass and "FHFMA" in sass and "SYNCS" in sass, k      # TMA bulk copy, 16-bit x 16-bit -> fp32 FMA
+        assert "UTMALDG.2D.GATHER4" in sass, k                                  # sparse filters: four rows per TMA instruction
     for k, sass in kernels("maxsim_tc5_kernel").items():
         assert "UTMALDG" in sass and "UTCHMMA.2CTA" in sass and "LDTM" in sass, k    # TMA tensor load, pair tcgen05.mma, tcgen05.ld
         assert "UTCBAR.2CTA.MULTICAST" in sass and "ELECT" in sass, k                # multicast commit, elect.sync issue block

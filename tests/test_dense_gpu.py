@@ -71,6 +71,18 @@ def test_guided_work_distribution_shapes(engine, n, d, k):
     _check(engine, corpus, query, k)
 
 
+@pytest.mark.parametrize("n,d,p", [(70_001, 16, 0.2), (50_000, 48, 0.1), (50_000, 80, 0.3), (40_003, 136, 0.1),
+                                   (60_000, 512, 0.1), (120_000, 1024, 0.05), (20_000, 2048, 0.1)])
+def test_sparse_filter_gather_tiles(engine, n, d, p):
+    """Sparse filters: passing rows of sparse mask words travel as gather tiles — four rows per TMA tile::gather4
+    through the row tensor map when d % 16 == 0 and d <= 1024, one bulk copy per run of rows otherwise (d = 136,
+    2048 here) and for the last partial tile.  Reference: the payload filter of vectorstore.py:188-197."""
+    corpus, query = make_dense_case(300 + d, n, d)
+    _check(engine, corpus, query, 10, bernoulli_mask(d, n, p))
+    runs = (np.arange(n) // 3) % 7 == 0  # runs of three passing rows: gather tiles straddle runs
+    _check(engine, corpus, query, 17, runs)
+
+
 def test_back_to_back_launches_share_nothing(engine):
     """40 queries in one call (chained launches under programmatic dependent launch, rotating work counters and
     alternating workspaces), three times over: every query's result equals its own single-launch result."""

@@ -103,6 +103,30 @@ def test_dense_oracle_against_bruteforce_loops():
     np.testing.assert_allclose(s, [v for v, _ in brute], rtol=1e-5, atol=1e-6)
 
 
+def test_dense_oracle_agrees_with_independent_cosine_knn_libraries():
+    """The dense oracle stays PARITY UNPINNED against the reference (qdrant-client is absent, oracle/dense.py), but it
+    is not alone: two independent exact-cosine implementations installed here — scikit-learn's brute-force
+    NearestNeighbors(metric="cosine") and scipy's cdist — return the same ids and scores on unnormalised fp32 rows
+    (inv_norm path) and on unit rows, with and without a filter."""
+    from scipy.spatial.distance import cdist
+    from sklearn.neighbors import NearestNeighbors
+
+    rng = np.random.default_rng(11)
+    for n, d, k, p in ((4000, 96, 10, 1.0), (3001, 1024, 25, 0.4), (513, 8, 100, 0.7)):
+        c = (rng.standard_normal((n, d)) * rng.uniform(0.2, 3.0, size=(n, 1))).astype(np.float32)
+        q = rng.standard_normal(d).astype(np.float32)
+        bits = rng.random(n) < p
+        inv = (1.0 / np.linalg.norm(c.astype(np.float64), axis=1)).astype(np.float32)
+        s, i = odense.topk(c, q, k, bits, inv_norm=inv)
+        rows = np.flatnonzero(bits)
+        nn = NearestNeighbors(n_neighbors=k, algorithm="brute", metric="cosine").fit(c[rows].astype(np.float64))
+        dist, idx = nn.kneighbors(q[None].astype(np.float64))
+        assert i.tolist() == rows[idx[0]].tolist()
+        np.testing.assert_allclose(s, 1.0 - dist[0], rtol=2e-5, atol=2e-6)
+        full = 1.0 - cdist(q[None].astype(np.float64), c.astype(np.float64), metric="cosine")[0]
+        np.testing.assert_allclose(odense.scores_f32(c, q, odense.COSINE, inv), full, rtol=2e-5, atol=2e-6)
+
+
 def test_dense_oracle_padding_and_ties():
     c = torch.zeros(6, 8, dtype=torch.float16)
     c[:, 0] = 1.0  # six identical rows -> six exactly tied scores
