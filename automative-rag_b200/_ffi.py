@@ -36,6 +36,7 @@ SIGNATURES = {
     "rs_set_maxsim_impl": (C.c_int, [_P, C.c_int]),
     "rs_set_scan_trace": (C.c_int, [_P, _P]),
     "rs_scan_plan": (C.c_int, [_I32, _I32, C.POINTER(_I64)]),
+    "rs_scan_plan_chained": (C.c_int, [_I32, _I32, C.POINTER(_I64)]),
     "rs_set_profiling": (C.c_int, [_P, C.c_int]),
     "rs_last_call_stats": (C.c_int, [_P, _P]),
     "rs_last_dense_impl": (C.c_int, [_P]),

@@ -600,7 +600,14 @@ struct ScanPlan {
   size_t smem;
 };
 
-static ScanPlan scan_plan(int d, int k) {
+// coresident: size the CTA for HALF an SM.  Inside one rs_dense_topk call the launches are chained (programmatic
+// dependent launch), and a full-SM CTA leaves its SM idle from its final compaction to the next query's first tile
+// (~7 us per query: compaction, publish, launch, barrier init, prologue, first TMA round trip).  With two CTAs per SM
+// query j+1 streams while query j finishes and starts: the same 24 tiles in flight per SM, no idle gap —
+// 1M x 1024, 64 queries per call: 293 -> 279 us per query; 125 k rows (one GPU's share of 1M at 8 GPUs): the fixed
+// cost was a quarter of the launch.  A lone launch on half a ring is much slower (305 -> 416 us), so the plan is
+// used for every launch of an unfiltered multi-query call and never for a single-query call.
+static ScanPlan scan_plan(int d, int k, bool coresident = false) {
   static const int max_slots = env_int("RS_SCAN_STAGES", kScanMaxStages);
   ScanPlan pl{};
   pl.tile_rows = scan_tile_rows(d);
@@ -614,8 +621,9 @@ static ScanPlan scan_plan(int d, int k) {
   const size_t fixed = (size_t)pl.buf_cap * 8 + 2 * kScanMaxStages * 8 + 8 + 16 + kScanMaxStages * 4 +
                        kScanMaxStages * 32 * 4 + kRowQueue * 4;
   const size_t tile_bytes = (size_t)pl.tile_rows * d * 2;
-  const size_t budget = 227 * 1024 - 1024;  // leave 1 KB for the runtime's reserved shared memory
-  int s = (int)((budget - fixed) / tile_bytes);
+  // leave 1 KB per CTA for the runtime's reserved shared memory (228 KB per SM in all)
+  const size_t budget = coresident ? (228 * 1024) / 2 - 1024 - 512 : 227 * 1024 - 1024;
+  int s = budget > fixed ? (int)((budget - fixed) / tile_bytes) : 0;
   s = s > kScanMaxStages ? kScanMaxStages : s;
   s = s > max_slots ? max_slots : s;
   if (s < 2) s = 2;
@@ -632,10 +640,20 @@ static ScanPlan scan_plan(int d, int k) {
   return pl;
 }
 
+// Two CTAs per SM need <= 73 registers per thread at 448 threads (the d <= 1024 instantiations; tests/test_abi.py
+// checks the built library) and a ring that still covers the HBM latency: >= 12 slots of 8 KB in each half.
+bool scan_coresident_ok(int d, int k) {
+  static const bool off = getenv("RS_SCAN_NO_CORESIDENT") != nullptr;
+  if (off || d > 1024) return false;
+  const ScanPlan pl = scan_plan(d, k, true);
+  return pl.stages >= 12 && (size_t)pl.tile_rows * d * 2 >= 4096 && pl.smem <= (228 * 1024) / 2 - 1024;
+}
+
 int scan_stages(int d, int k) { return scan_plan(d, k).stages; }
 
-void scan_plan_query(int d, int k, int64_t out[7]) {
-  const ScanPlan pl = scan_plan(d, k);
+void scan_plan_query(int d, int k, int64_t out[7], bool chained) {
+  const bool co = chained && scan_coresident_ok(d, k);
+  const ScanPlan pl = scan_plan(d, k, co);
   out[0] = pl.tile_rows;
   out[1] = pl.consumers;
   out[2] = pl.stages;
@@ -643,6 +661,7 @@ void scan_plan_query(int d, int k, int64_t out[7]) {
   out[4] = pl.buf_hw;
   out[5] = pl.rounds_per_check;
   out[6] = (int64_t)pl.smem;
+  if (chained) out[7] = co ? 1 : 0;
 }
 
 size_t scan_smem_bytes(int d, int k) { return scan_plan(d, k).smem; }
@@ -663,8 +682,10 @@ bool scan_gather4_supported(int d) {
 }
 
 cudaError_t launch_dense_scan(ScanParams p, int dtype, int num_sms, bool pdl, cudaStream_t stream,
-                              const CUtensorMap* gather_map) {
-  const ScanPlan pl = scan_plan(p.d, p.k);
+                              const CUtensorMap* gather_map, bool chained) {
+  // Filtered calls keep the full-SM plan: gather tiles (four random rows each) have a longer round trip, and a
+  // 12-slot half ring costs p = 0.5 / 0.25 filters 14 % / 9 % (profiles/r02_scan_coresident_ab.txt).
+  const ScanPlan pl = scan_plan(p.d, p.k, chained && p.mask == nullptr && scan_coresident_ok(p.d, p.k));
   alignas(64) CUtensorMap gmap;
   if (gather_map != nullptr && p.mask != nullptr && scan_gather4_supported(p.d)) {
     gmap = *gather_map;

@@ -39,14 +39,17 @@ int scan_tile_rows(int d);
 size_t scan_smem_bytes(int d, int k);
 // shared-memory plan of a scan launch: out[0..6] = tile_rows, consumers, stages, buf_cap, buf_hw, rounds_per_check,
 // dynamic shared-memory bytes (host-only arithmetic; exported through rs_scan_plan for the CPU tests)
-void scan_plan_query(int d, int k, int64_t out[7]);
+// chained: the plan of a launch inside a multi-query call (two CTAs per SM when scan_coresident_ok); then out has 8
+// entries and out[7] = 1 when the co-resident plan applies
+void scan_plan_query(int d, int k, int64_t* out, bool chained = false);
+bool scan_coresident_ok(int d, int k);
 // pdl: launch with programmatic stream serialization (only between consecutive scans of one call,
 // whose inputs are all complete before the first launch; see dense_scan.cu)
 // gather_map: tensor map of the corpus as [n][2d / 8] 8-byte elements, box = one row (tc5_encode_rows), or null:
 // with a filter mask the passing rows of sparse mask words are then fetched four per TMA instruction.
 bool scan_gather4_supported(int d);
 cudaError_t launch_dense_scan(ScanParams p, int dtype, int num_sms, bool pdl, cudaStream_t stream,
-                              const CUtensorMap* gather_map = nullptr);
+                              const CUtensorMap* gather_map = nullptr, bool chained = false);
 
 // ------------------------------------------------------------------ top-k list merge
 cudaError_t launch_topk_merge(const float* scores, const int64_t* ids, int nlists, int nq, int k_in, int k_out,

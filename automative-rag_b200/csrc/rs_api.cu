@@ -269,6 +269,11 @@ int rs_scan_plan(int32_t d, int32_t k, int64_t* out7) {
   rs::scan_plan_query(d, k, out7);
   return RS_OK;
 }
+int rs_scan_plan_chained(int32_t d, int32_t k, int64_t* out8) {
+  if (!out8 || d <= 0 || (d % 8) != 0 || d > 4096 || k < 1 || k > kMaxK) return RS_ERR_INVALID_ARG;
+  rs::scan_plan_query(d, k, out8, /*chained=*/true);
+  return RS_OK;
+}
 int rs_set_profiling(rs_handle* h, int on) {
   if (!h) return RS_ERR_INVALID_ARG;
   DeviceGuard guard(h->device);
@@ -376,7 +381,7 @@ int rs_dense_topk(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_
     p.out_ids = out_ids + (size_t)qi * k;
     const int ctr = (int)((h->scan_seq - 1) & (kScanCounters - 1));
     p.unit_counter = h->unit_ctr + ctr;
-    cudaError_t e = rs::launch_dense_scan(p, dtype, h->num_sms, /*pdl=*/qi > 0, st, gather_map);
+    cudaError_t e = rs::launch_dense_scan(p, dtype, h->num_sms, /*pdl=*/qi > 0, st, gather_map, /*chained=*/nq > 1);
     if (e != cudaSuccess) return cuda_fail(h, e, "dense_scan_kernel launch");
     h->launches += 1;
   }

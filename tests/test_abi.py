@@ -66,6 +66,40 @@ def test_scan_shared_memory_plan_invariants():
     assert lib.rs_scan_plan(12, 10, out) != 0 and lib.rs_scan_plan(1024, 0, out) != 0 and lib.rs_scan_plan(1024, 4096, out) != 0
 
 
+def test_chained_scan_plan_fits_two_ctas_per_sm():
+    """Launches inside a multi-query call are sized for HALF an SM where that keeps a 12-slot ring (rs_scan_plan_chained):
+    2 x (dynamic + 1 KB reserved) <= 228 KB of shared memory, and the d <= 1024 instantiations of the kernel must stay
+    within the 73 registers per thread that two 448-thread CTAs leave each other (read from the built library)."""
+    import ctypes as C
+    import subprocess
+
+    lib = rag.load_library()
+    lone, out = (C.c_int64 * 7)(), (C.c_int64 * 8)()
+    seen = set()
+    for d in range(8, 4097, 8):
+        for k in (1, 10, 100, 128, 170, 171, 500, 1000, 2048):
+            assert lib.rs_scan_plan(d, k, lone) == 0 and lib.rs_scan_plan_chained(d, k, out) == 0
+            co = out[7]
+            assert co in (0, 1)
+            seen.add(co)
+            if co:
+                assert d <= 1024 and out[2] >= 12 and 2 * (out[6] + 1024) <= 228 * 1024
+                assert out[1] <= out[2] and list(out)[3:6] == list(lone)[3:6]   # same top-k buffer as the lone plan
+            else:
+                assert list(out)[:7] == list(lone)
+    assert seen == {0, 1}
+    assert lib.rs_scan_plan_chained(1024, 10, out) == 0 and out[7] == 1         # the headline shape is co-resident
+    assert lib.rs_scan_plan_chained(1024, 1000, out) == 0 and out[7] == 0       # config 5 stage 1 keeps the full SM
+    so = os.path.join(ROOT, "automative-rag_b200", "lib", "librag_b200.so")
+    usage = subprocess.run(["cuobjdump", "-res-usage", so], capture_output=True, text=True, check=True).stdout
+    regs = {}
+    for fn, reg in re.findall(r"Function (\S*dense_scan_kernel\S*):\s*\n\s*REG:(\d+)", usage):
+        nch = int(re.search(r"Li(\d+)E", fn).group(1))
+        regs[nch] = max(regs.get(nch, 0), int(reg))
+    assert set(regs) == {1, 2, 4, 8, 16}, regs
+    assert all(regs[n] <= 73 for n in (1, 2, 4)), regs
+
+
 def test_library_loads_and_reports_abi_version():
     lib = rag.load_library()
     assert lib.rs_abi_version() == 2
