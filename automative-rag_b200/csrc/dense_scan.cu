@@ -169,7 +169,8 @@ __global__ void __launch_bounds__(kScanThreads, 1)
     int slot = 0, posmod = 0;
     uint32_t phase = 0;
     uint32_t head = 0, tail = 0;  // row queue (warp-uniform)
-    const int batch_max = min(S, 8);  // tiles issued per warp pass, one per lane
+    const int batch_max = min(S, p.batch_max);  // contiguous tiles issued per warp pass, one per lane
+    const int gather_batch = min(S, p.gather_batch);  // gather tiles per pass
 
     auto word_bits = [&](int64_t gw) -> uint32_t {  // filter bits of global mask word gw
       if (gw >= num_words) return 0u;
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(kScanThreads, 1)
       __syncwarp();
       int full_tiles = (int)(tail - head) / tile_rows;
       while (full_tiles > 0) {
-        const int nt = min(full_tiles, min(batch_max, 32 >> lanes_per_tile_shift));
+        const int nt = min(full_tiles, min(gather_batch, 32 >> lanes_per_tile_shift));
         issue_gather(nt, tile_rows);
         full_tiles -= nt;
       }
@@ -606,7 +607,7 @@ struct ScanPlan {
 // query j+1 streams while query j finishes and starts: the same 24 tiles in flight per SM, no idle gap —
 // 1M x 1024, 64 queries per call: 293 -> 279 us per query; 125 k rows (one GPU's share of 1M at 8 GPUs): the fixed
 // cost was a quarter of the launch.  A lone launch on half a ring is much slower (305 -> 416 us), so the plan is
-// used for every launch of an unfiltered multi-query call and never for a single-query call.
+// used for every launch of a multi-query call and never for a single-query call.
 static ScanPlan scan_plan(int d, int k, bool coresident = false) {
   static const int max_slots = env_int("RS_SCAN_STAGES", kScanMaxStages);
   ScanPlan pl{};
@@ -683,9 +684,16 @@ bool scan_gather4_supported(int d) {
 
 cudaError_t launch_dense_scan(ScanParams p, int dtype, int num_sms, bool pdl, cudaStream_t stream,
                               const CUtensorMap* gather_map, bool chained) {
-  // Filtered calls keep the full-SM plan: gather tiles (four random rows each) have a longer round trip, and a
-  // 12-slot half ring costs p = 0.5 / 0.25 filters 14 % / 9 % (profiles/r02_scan_coresident_ab.txt).
-  const ScanPlan pl = scan_plan(p.d, p.k, chained && p.mask == nullptr && scan_coresident_ok(p.d, p.k));
+  const bool co = chained && scan_coresident_ok(p.d, p.k);
+  const ScanPlan pl = scan_plan(p.d, p.k, co);
+  // Ring slots the producer claims per pass.  It waits for ALL of them before issuing any, so on the 12-slot half
+  // ring a pass of 8 gather tiles (four random rows each: the longest round trip) stalls on the slowest slot of two
+  // thirds of the ring: p = 0.5 / 0.25 / 0.1 ran at 0.82 / 0.81 / 0.78 of HBM with 8 and at 1.00 / 0.99 / 0.87 with 4
+  // (2: 1.03 / 1.00 / 0.90 but p = 0.03 0.74 -> 0.64).  The 26-slot ring and contiguous tiles are best with 8
+  // (profiles/r02_scan_coresident_ab.txt).
+  static const int batch_env = env_int("RS_SCAN_BATCH", 0), gbatch_env = env_int("RS_SCAN_GATHER_BATCH", 0);
+  p.batch_max = batch_env > 0 ? (batch_env > 8 ? 8 : batch_env) : 8;
+  p.gather_batch = gbatch_env > 0 ? (gbatch_env > 8 ? 8 : gbatch_env) : (co ? 4 : 8);
   alignas(64) CUtensorMap gmap;
   if (gather_map != nullptr && p.mask != nullptr && scan_gather4_supported(p.d)) {
     gmap = *gather_map;

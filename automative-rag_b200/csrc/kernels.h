@@ -33,6 +33,8 @@ struct ScanParams {
   int32_t grab_max;        // largest grab in mask words (<= 32), filled by the launcher
   int32_t first_words;     // words per CTA handed out statically before the counter is used (0 = none)
   uint64_t* trace;         // diagnostics (rs_set_scan_trace): [grid][8] %globaltimer stamps, or null
+  int32_t batch_max;       // filled by the launcher: ring slots claimed per producer pass, contiguous tiles (<= 8)
+  int32_t gather_batch;    // same for gather tiles
   int32_t gather4;         // filled by the launcher: gather tiles go out as TMA tile::gather4 (row tensor map given)
 };
 int scan_tile_rows(int d);

@@ -124,7 +124,7 @@ int rs_set_scan_trace(rs_handle* h, uint64_t* trace_dev);
  */
 int rs_scan_plan(int32_t d, int32_t k, int64_t* out7);
 /*
- * The plan of a launch inside an unfiltered multi-query rs_dense_topk call (its launches are chained): out8[0..6] as
+ * The plan of a launch inside a multi-query rs_dense_topk call (its launches are chained): out8[0..6] as
  * above, out8[7] = 1 when the CTA is sized for half an SM so that consecutive queries' CTAs share an SM and one query's
  * start-up and wind-down overlap its neighbour's streaming (d <= 1024 and k small enough for a 12-slot half ring),
  * 0 when the call uses the single-launch plan.
