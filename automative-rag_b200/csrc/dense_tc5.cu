@@ -78,6 +78,8 @@ struct DenseTcParams {
   int32_t bootstrap;        // 1 = bisect a first threshold out of each range's first tile (0: RS_DENSE_NO_BOOTSTRAP)
   int32_t cross_groups;     // ceil(k / gm) <= min(num_ranges, kDtMaxGroups): the cross-CTA threshold is the minimum over these
   long long* trace;         // diagnostics (RS_DENSE_TRACE=1): [CTAs][16] cycles each role spent waiting, or null
+  int32_t* progress;        // [num_ranges, query groups]: corpus tiles whose loads a (range, group) has issued (0 at launch)
+  int32_t drift;            // a group loads at most this many tiles ahead of the slowest group of its range (0 = free)
 };
 
 // wait (+ cycles spent waiting when a trace buffer is attached)
@@ -217,8 +219,22 @@ __global__ void __launch_bounds__(kDtThreads, 1)
       int it = 0;
       const long long T0 = clock64();
       long long w_empty = 0;
+      const int ngroups = (int)gridDim.y;
       for (int ti = 0; ti < ntiles; ++ti) {
         const int t = range + ti * p.num_ranges;
+        // Keep the query groups of a range within p.drift tiles of each other: every group streams the SAME corpus
+        // tiles, and a tile is served from L2 to the followers only while the leader is not further ahead than the L2
+        // holds (free-running groups drifted apart over the ~2000 tiles of a range: 2.4-2.7x the corpus from DRAM).
+        // Purely a pacing hint: the poll is bounded, so a group that cannot see its peers simply goes on.
+        if (p.drift > 0 && ngroups > 1 && ti >= p.drift) {
+          const volatile int32_t* pr = p.progress + (size_t)range * ngroups;
+          for (int spin = 0; spin < 4096; ++spin) {
+            int lo = 0x7fffffff;
+            for (int g = 0; g < ngroups; ++g) lo = min(lo, (int)pr[g]);
+            if (lo + p.drift >= ti) break;
+            __nanosleep(200);
+          }
+        }
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (uint32_t)(it / kStages) & 1u;
@@ -241,6 +257,8 @@ __global__ void __launch_bounds__(kDtThreads, 1)
               tma_load_2d(st + kMT * kDtABytes, &map_c, kb * kDtBK, t * kDtBN, &full[s], pol);
           }
         }
+        if (p.drift > 0 && ngroups > 1 && rank == 0 && lane == nbox - 1)
+          *(volatile int32_t*)(p.progress + (size_t)range * ngroups + mgroup) = ti + 1;
       }
       if (tracing && lane == 0) {
         p.trace[cta_linear * 16 + 10] = w_empty;
@@ -719,8 +737,9 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
   const size_t ls_bytes = ((size_t)ranges * nq * k_list * sizeof(float) + 255) / 256 * 256;
   const size_t li_bytes = ((size_t)ranges * nq * k_list * sizeof(int64_t) + 255) / 256 * 256;
   const size_t gt_bytes = ((size_t)ranges * nq * sizeof(uint32_t) + 255) / 256 * 256;
-  const size_t qs_bytes = (size_t)nq * sizeof(float);
-  uint8_t* ws = static_cast<uint8_t*>(tc5_dense_scratch(s, cand_bytes + ls_bytes + li_bytes + gt_bytes + qs_bytes));
+  const size_t qs_bytes = ((size_t)nq * sizeof(float) + 255) / 256 * 256;
+  const size_t pr_bytes = ((size_t)ranges * mgroups * sizeof(int32_t) + 255) / 256 * 256;
+  uint8_t* ws = static_cast<uint8_t*>(tc5_dense_scratch(s, cand_bytes + ls_bytes + li_bytes + gt_bytes + qs_bytes + pr_bytes));
   if (!ws) {
     *err = "out of device memory for the candidate buffers";
     return -5;
@@ -745,6 +764,16 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
   kp.tiles_total = tiles_total;
   kp.gthr = reinterpret_cast<uint32_t*>(ws + cand_bytes + ls_bytes + li_bytes);
   kp.qscale_out = reinterpret_cast<float*>(ws + cand_bytes + ls_bytes + li_bytes + gt_bytes);
+  kp.progress = reinterpret_cast<int32_t*>(ws + cand_bytes + ls_bytes + li_bytes + gt_bytes + qs_bytes);
+  static const int drift = getenv("RS_DENSE_DRIFT") ? atoi(getenv("RS_DENSE_DRIFT")) : 2;
+  kp.drift = mgroups > 1 ? drift : 0;
+  if (kp.drift > 0) {
+    cudaError_t me = cudaMemsetAsync(kp.progress, 0, pr_bytes, stream);
+    if (me != cudaSuccess) {
+      *err = cudaGetErrorString(me);
+      return -3;
+    }
+  }
   static const int cross_off = getenv("RS_DENSE_NO_CROSS_THR") ? 1 : 0;  // A/B switch for scripts/batch_bench.py
   const int gm = std::max((k + ranges - 1) / ranges, (k + kDtMaxGroups - 1) / kDtMaxGroups);
   kp.gm = (ranges > 1 && gm <= kDtMaxGm && !cross_off) ? gm : 0;
