@@ -1,6 +1,7 @@
 """Small driver for ncu: a few launches of each hot kernel at BASELINE sizes.
 
     python scripts/profile_kernels.py scan      # dense_scan_kernel, 1M x 1024 fp16, top-10
+    python scripts/profile_kernels.py scan_p01  # same with a Bernoulli(0.1) filter (gather tiles)
     python scripts/profile_kernels.py maxsim    # maxsim_tc5_kernel, config 4a
     python scripts/profile_kernels.py maxsim_mma
     python scripts/profile_kernels.py maxsim_cand # maxsim_cand_tc5_kernel, config 4b
@@ -25,6 +26,17 @@ if what == "scan":
     c = torch.randn(n, d, generator=g, device=dev, dtype=torch.float16)
     q = torch.randn(d, generator=g, device=dev, dtype=torch.float16)
     mask = torch.full(((n + 31) // 32,), -1, dtype=torch.int32, device=dev)
+    eng.set_dense_impl(_ffi.RS_DENSE_SCAN)
+    for _ in range(iters):
+        eng.dense_topk(c, q, 10, mask=mask)
+elif what == "scan_p01":  # sparse filter: gather tiles, four rows per TMA tile::gather4
+    import numpy as np
+    from automative_rag_b200.filters import pack_bits
+    n, d = 1_000_000, 1024
+    g = torch.Generator(device=dev).manual_seed(1)
+    c = torch.randn(n, d, generator=g, device=dev, dtype=torch.float16)
+    q = torch.randn(d, generator=g, device=dev, dtype=torch.float16)
+    mask = torch.from_numpy(pack_bits(np.random.default_rng(3).random(n) < 0.1)).to(dev)
     eng.set_dense_impl(_ffi.RS_DENSE_SCAN)
     for _ in range(iters):
         eng.dense_topk(c, q, 10, mask=mask)
