@@ -22,6 +22,7 @@ struct TopKBuffer {
   int C, hw, k;       // capacity, high-water mark (C - slack), list length
   int tid, nthreads;  // participating threads (named barrier `bar_id`)
   int bar_id;
+  uint64_t floor_key = 0ull;  // a key known to be <= the final k-th best (raise_floor); the threshold never drops below it
 
   __device__ __forceinline__ int high_water() const { return hw; }
   __device__ __forceinline__ int slack() const { return C - hw; }
@@ -73,8 +74,17 @@ struct TopKBuffer {
     if (tid == 0) {
       int kept = min(n, k);
       *cnt = kept;
-      *thr = (kept == k) ? keys[k - 1] : 0ull;
+      const uint64_t kth = (kept == k) ? keys[k - 1] : 0ull;
+      *thr = kth > floor_key ? kth : floor_key;
     }
+    named_bar_sync(bar_id, nthreads);
+  }
+
+  // all participating threads, same `bound`: the caller knows that at least k keys of the whole stream are > bound
+  // (so nothing <= bound can be in the answer).  Keys already in the buffer stay; they are sorted out by compact().
+  __device__ __forceinline__ void raise_floor(uint64_t bound) {
+    floor_key = bound;
+    if (tid == 0 && bound > *thr) *thr = bound;
     named_bar_sync(bar_id, nthreads);
   }
 

@@ -14,8 +14,10 @@ g = torch.Generator(device=dev).manual_seed(1)
 c = torch.randn(1_000_000, d, generator=g, device=dev, dtype=torch.float16)
 trace = torch.zeros(8, sms, 8, dtype=torch.int64, device=dev)
 NAMES = ["entry", "bar_init", "prologue", "first_tile", "stream", "compact", "publish", "merge"]
-for k in (10, 100):
-    for n in (4736, 62_500, 125_000, 250_000, 1_000_000):
+KS = tuple(int(x) for x in sys.argv[1].split(",")) if len(sys.argv) > 1 else (10, 100)
+NS = tuple(int(x) for x in sys.argv[2].split(",")) if len(sys.argv) > 2 else (4736, 62_500, 125_000, 250_000, 1_000_000)
+for k in KS:
+    for n in NS:
         for nq in (1, 8):
             q = torch.randn(nq, d, generator=g, device=dev, dtype=torch.float16)
             eng.set_scan_trace(None)
