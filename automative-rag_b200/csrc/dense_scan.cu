@@ -57,7 +57,8 @@ constexpr int kConsumerBar = 1;   // named barrier id for the consumer threads
 constexpr int kRowQueue = 2048;   // pending passing rows (power of two >= 32 words x 32 rows + a tile)
 constexpr int kSlotContig = 0x100;  // slot_n flag: row ids are slot_rows[0] + lane (else slot_rows[lane])
 constexpr int kSlotEnd = -1;
-constexpr int kTournamentMaxK = 32;   // cross-CTA merge: tournament up to this k (~0.15 us per result), streaming compaction above
+constexpr int kTournamentMaxK = 48;   // cross-CTA merge: tournament up to this k (~0.15 us per result + 1.5 us; the deployed
+                                      // k of 20-40, mode_config.py), streamed merge above (11-13 us at k = 33..100)
 constexpr int kTournamentLists = 5;   // lists per lane of the tournament warp (grid <= 160)
 constexpr int kDenseWordBits = 24;  // words with >= 24 of 32 rows passing are staged whole (<= 25% extra bytes)
 

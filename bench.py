@@ -605,7 +605,7 @@ def extra_single_gpu(cx, corpus, queries):
         out["dense_batch_config3"] = {
             "ms_per_batch": ms, "queries_per_s": nq3 / ms * 1e3, "rows": n3, "queries": nq3, "k": k3,
             "roofline": {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": cx.tf_sustained, "unit": "TFLOP/s",
-                         "frac": fl / ms / 1e9 / cx.tf_sustained, "traffic": None,
+                         "frac": fl / ms / 1e9 / cx.tf_sustained, "traffic": committed_traffic("dense_tc5.cu", "config3"),
                          "peak_source": "measured sustained" if "bf16_tflops_sustained" in peaks else "fallback"}}
         if not cx.args.no_parity:
             out["dense_batch_config3"].update(parity_config3(eng, c3, q3, k3))

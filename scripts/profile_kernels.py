@@ -59,10 +59,12 @@ elif what == "maxsim_cand":
     eng.set_maxsim_impl(_ffi.RS_MAXSIM_TCGEN05_CAND)
     for _ in range(iters):
         eng.maxsim(q, toks, off, cand=cand)
-elif what == "dense_batch":
-    n, d, nq, k = 2_000_000, 1024, 1024, 100
+elif what in ("dense_batch", "dense_batch_10m"):  # dense_batch_10m = BASELINE config 3 at its full size
+    n, d, nq, k = (2_000_000 if what == "dense_batch" else 10_000_000), 1024, 1024, 100
     g = torch.Generator(device=dev).manual_seed(4)
-    c = torch.randn(n, d, generator=g, device=dev, dtype=torch.bfloat16)
+    c = torch.empty(n, d, device=dev, dtype=torch.bfloat16)
+    for lo in range(0, n, 1_000_000):
+        c[lo:lo + 1_000_000] = torch.randn(min(1_000_000, n - lo), d, generator=g, device=dev).bfloat16()
     q = torch.randn(nq, d, generator=g, device=dev, dtype=torch.bfloat16)
     eng.set_dense_impl(_ffi.RS_DENSE_TCGEN05)
     for _ in range(iters):

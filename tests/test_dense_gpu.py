@@ -61,10 +61,10 @@ def test_mask_edge_patterns(engine):
 
 
 @pytest.mark.parametrize("n,d,k", [(200_003, 64, 10), (150_000, 128, 33), (400_001, 256, 32), (90_000, 1024, 32),
-                                   (90_000, 1024, 33), (33, 1024, 10), (4737, 1024, 10)])
+                                   (90_000, 1024, 33), (90_000, 1024, 48), (90_000, 1024, 49), (33, 1024, 10), (4737, 1024, 10)])
 def test_guided_work_distribution_shapes(engine, n, d, k):
     """Shapes that exercise the scan's work counter and both cross-CTA merges: small d (a grab is several mask words,
-    32-row tiles), many grabs per CTA, k on both sides of the tournament limit (32), fewer words than SMs."""
+    32-row tiles), many grabs per CTA, k on both sides of the tournament limit (48; 32 / 33 were its round-1 sides), fewer words than SMs."""
     corpus, query = make_dense_case(77 + n, n, d)
     bits = bernoulli_mask(n, n, 0.6)
     _check(engine, corpus, query, k, bits)
