@@ -40,6 +40,7 @@ SIGNATURES = {
     "rs_set_profiling": (C.c_int, [_P, C.c_int]),
     "rs_last_call_stats": (C.c_int, [_P, _P]),
     "rs_last_dense_impl": (C.c_int, [_P]),
+    "rs_last_dense_redo": (C.c_int, [_P]),
     "rs_last_maxsim_impl": (C.c_int, [_P]),
     "rs_dense_topk": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _I32, _P, _I64, _I32, _I64, _P, _P, _P]),
     "rs_dense_topk_host": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _I32, _P, _P, _I64, _I32, _I64, _P, _P, _P]),
@@ -189,6 +190,11 @@ class Engine:
     @property
     def last_dense_impl(self) -> int:
         return int(self._lib.rs_last_dense_impl(self._h))
+
+    @property
+    def last_dense_redo(self) -> int:
+        """Queries the last batched call with k > 128 re-ran through the exact single-query scan."""
+        return int(self._lib.rs_last_dense_redo(self._h))
 
     @property
     def last_maxsim_impl(self) -> int:

@@ -680,6 +680,80 @@ __global__ void __launch_bounds__(kDtThreads, 1)
   }
 }
 
+// ------------------------------------------------------------------ lists longer than a range may keep (k > 128)
+// For 128 < k <= 1024 the kernel keeps only the k_run <= 128 best rows of every corpus range (ranges are interleaved
+// 256-row tiles, so each holds ~k / ranges of a query's top k) and the merge takes the k best of ranges * k_list
+// candidates.  That is exact unless some range held MORE than it could keep: a range whose list is full (>= k_run
+// valid entries) and whose weakest kept score is not below the merged k-th score may have dropped a row of the answer.
+// This kernel flags such queries; the caller re-runs them through the single-query scan (never seen on random data:
+// the expected share of a range is k / ranges against k_run slots; thousands of exactly tied scores do trigger it).
+__global__ void __launch_bounds__(256) dense_overflow_check_kernel(const float* __restrict__ list_scores,
+                                                                   const int64_t* __restrict__ list_ids, int ranges,
+                                                                   int nq, int k_list, int k_run,
+                                                                   const float* __restrict__ out_scores,
+                                                                   const int64_t* __restrict__ out_ids, int k,
+                                                                   int32_t* __restrict__ flags) {
+  const int q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // merged k-th score; fewer than k results = nothing may have been dropped anywhere
+  const bool have_k = out_ids[(size_t)q * k + (k - 1)] >= 0;
+  const float kth = have_k ? out_scores[(size_t)q * k + (k - 1)] : -CUDART_INF_F;
+  if (threadIdx.x == 0) flags[q] = 0;
+  __syncthreads();
+  for (int r = warp; r < ranges; r += 8) {
+    const size_t base = ((size_t)r * nq + q) * k_list;
+    int cnt = 0;
+    float lo = CUDART_INF_F;
+    for (int j = lane; j < k_list; j += 32) {
+      if (list_ids[base + j] >= 0) {
+        ++cnt;
+        lo = fminf(lo, list_scores[base + j]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+      lo = fminf(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
+    }
+    if (lane == 0 && cnt >= k_run && lo >= kth) flags[q] = 1;
+  }
+}
+
+// Sizing shared by tc5_dense_supported and tc5_dense_topk.
+struct DtPlan {
+  bool pair, two_level;
+  int mgroups, tiles_total, ranges, k_run, k_list;
+};
+static bool dt_plan(int num_sms, int64_t n, int nq, int k, DtPlan* pl) {
+  static const int no_pair = getenv("RS_DENSE_NO_PAIR") ? 1 : 0;  // A/B switch for scripts/batch_bench.py
+  // pairs cover 256 queries; up to 128 queries fit one CTA's single M tile, where a pair's second CTA would idle
+  pl->pair = !no_pair && num_sms >= 2 && nq > 128;
+  pl->mgroups = (nq + kDtMT * 128 - 1) / (kDtMT * 128);  // 256 queries per CTA / per CTA pair
+  pl->tiles_total = (int)((n + kDtBN - 1) / kDtBN);
+  int ranges = (pl->pair ? num_sms / 2 : num_sms) / pl->mgroups;
+  if (ranges < 1) ranges = 1;
+  if (ranges > pl->tiles_total) ranges = pl->tiles_total;
+  pl->two_level = k > 128;
+  if (!pl->two_level) {
+    // slots per (range, query) list: k plus slack, so that a threshold with [k, k_list] keys above it is easy to
+    // find; ranges * k_list keys per query must fit rs_topk_merge's shared memory
+    int k_list = std::max(32, k + std::max(k / 2, 22));
+    if ((long long)ranges * k_list > 16384) k_list = std::max(k, 16384 / ranges);
+    while ((long long)ranges * k_list > 16384) --ranges;
+    pl->ranges = ranges;
+    pl->k_run = k;
+    pl->k_list = k_list;
+    return true;
+  }
+  if (k > 1024 || ranges < 2) return false;
+  const int kl_max = 16384 / ranges;                      // >= 110 for <= 148 ranges
+  const int k_run = std::min(128, kl_max * 4 / 5);
+  pl->ranges = ranges;
+  pl->k_run = k_run;
+  pl->k_list = std::min(kl_max, k_run + std::max(k_run / 2, 22));
+  // a range must be able to hold twice its expected share of the answer (the rest is the overflow check's business)
+  return k_run >= 32 && 2ll * k <= (long long)ranges * k_run;
+}
+
 // ================================================================================ host side
 bool tc5_dense_supported(const Tc5State* s, int64_t n, int d, int nq, int k, const uint32_t* mask,
                          int64_t mask_stride_words, bool worthwhile) {
@@ -694,30 +768,31 @@ bool tc5_dense_supported(const Tc5State* s, int64_t n, int d, int nq, int k, con
   // `worthwhile` (the AUTO choice) adds the profitability rule to what the kernel can do
   if (worthwhile && (min_nq > 0 ? nq < min_nq : (nq < 4 && n < 200000))) return false;
   if (d % kDtBK != 0 || d < kDtBK) return false;
-  if (k > 128) return false;
   (void)mask_stride_words;                       // a filter per query is a per-thread mask word in the epilogue
   if (n >= (1ll << 31) * (int64_t)1) return false;
-  return true;
+  DtPlan pl;
+  return dt_plan(tc5_num_sms(s), n, nq, k, &pl);  // k <= 128 directly, k <= 1024 through the two-level lists
 }
 
 int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype, const float* inv_norm, int metric,
                    const void* queries, int nq, const uint32_t* mask, int64_t mask_stride_words, int k, int64_t id_base, float* out_scores,
-                   int64_t* out_ids, cudaStream_t stream, int* launched, std::string* err) {
+                   int64_t* out_ids, cudaStream_t stream, int* launched, std::string* err, std::vector<int>* redo) {
   *launched = 0;
+  if (redo) redo->clear();
   const int num_sms = tc5_num_sms(s);
-  static const int no_pair = getenv("RS_DENSE_NO_PAIR") ? 1 : 0;  // A/B switch for scripts/batch_bench.py
-  // pairs cover 256 queries; up to 128 queries fit one CTA's single M tile, where a pair's second CTA would idle
-  const bool pair = !no_pair && num_sms >= 2 && nq > 128;
-  const int mgroups = (nq + kDtMT * 128 - 1) / (kDtMT * 128);  // 256 queries per CTA / per CTA pair
-  const int tiles_total = (int)((n + kDtBN - 1) / kDtBN);
-  int ranges = (pair ? num_sms / 2 : num_sms) / mgroups;
-  if (ranges < 1) ranges = 1;
-  if (ranges > tiles_total) ranges = tiles_total;
-  // slots per (range, query) list: k plus slack, so that a threshold with [k, k_list] keys above it is easy to find;
-  // ranges * k_list keys per query must fit rs_topk_merge's shared memory
-  int k_list = std::max(32, k + std::max(k / 2, 22));
-  if ((long long)ranges * k_list > 16384) k_list = std::max(k, 16384 / ranges);
-  while ((long long)ranges * k_list > 16384) --ranges;
+  DtPlan pl;
+  if (!dt_plan(num_sms, n, nq, k, &pl)) {
+    *err = "unsupported (k, corpus) for the batched kernel";
+    return -2;
+  }
+  const bool pair = pl.pair;
+  const int mgroups = pl.mgroups, tiles_total = pl.tiles_total, ranges = pl.ranges, k_list = pl.k_list;
+  const int k_out = k;  // what the caller asked for
+  k = pl.k_run;         // what a range keeps (== k_out unless two_level)
+  if (pl.two_level && !redo) {
+    *err = "k > 128 needs a fallback list";
+    return -2;
+  }
 
   const int a_rows = nq < 128 ? (nq + 7) / 8 * 8 : 128;
   CUtensorMap map_q, map_c;
@@ -739,7 +814,9 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
   const size_t gt_bytes = ((size_t)ranges * nq * sizeof(uint32_t) + 255) / 256 * 256;
   const size_t qs_bytes = ((size_t)nq * sizeof(float) + 255) / 256 * 256;
   const size_t pr_bytes = ((size_t)ranges * mgroups * sizeof(int32_t) + 255) / 256 * 256;
-  uint8_t* ws = static_cast<uint8_t*>(tc5_dense_scratch(s, cand_bytes + ls_bytes + li_bytes + gt_bytes + qs_bytes + pr_bytes));
+  const size_t fl_bytes = ((size_t)nq * sizeof(int32_t) + 255) / 256 * 256;
+  uint8_t* ws = static_cast<uint8_t*>(
+      tc5_dense_scratch(s, cand_bytes + ls_bytes + li_bytes + gt_bytes + qs_bytes + pr_bytes + fl_bytes));
   if (!ws) {
     *err = "out of device memory for the candidate buffers";
     return -5;
@@ -776,7 +853,8 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
   }
   static const int cross_off = getenv("RS_DENSE_NO_CROSS_THR") ? 1 : 0;  // A/B switch for scripts/batch_bench.py
   const int gm = std::max((k + ranges - 1) / ranges, (k + kDtMaxGroups - 1) / kDtMaxGroups);
-  kp.gm = (ranges > 1 && gm <= kDtMaxGm && !cross_off) ? gm : 0;
+  // two-level lists: the cross-range bound would vouch for k_run rows, not for the k_out the caller wants — off
+  kp.gm = (ranges > 1 && gm <= kDtMaxGm && !cross_off && !pl.two_level) ? gm : 0;
   static const int bootstrap_off = getenv("RS_DENSE_NO_BOOTSTRAP") ? 1 : 0;
   kp.bootstrap = bootstrap_off ? 0 : 1;
   kp.cross_groups = kp.gm > 0 ? std::min(ranges, (k + kp.gm - 1) / kp.gm) : 1;
@@ -849,13 +927,29 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
             avg(5, 1), avg(6, 0), avg(6, 1), avg(7, 0), avg(8, 0), avg(9, 0), avg(12, 0), avg(11, 0), avg(11, 1), avg(10, 0), avg(10, 1), avg(13, -1), avg(14, -1));
   }
   // the lists are in no particular order; the kernel's final cross-range words bound the answer for the merge
-  e = launch_topk_merge(kp.list_scores, kp.list_ids, ranges, nq, k_list, k, 0, 0, out_scores, out_ids, stream,
+  e = launch_topk_merge(kp.list_scores, kp.list_ids, ranges, nq, k_list, k_out, 0, 0, out_scores, out_ids, stream,
                         kp.gm > 0 ? kp.gthr : nullptr, kp.cross_groups, kp.qscale_out);
   if (e != cudaSuccess) {
     *err = cudaGetErrorString(e);
     return -3;
   }
   *launched = 2;
+  if (pl.two_level) {
+    int32_t* flags = reinterpret_cast<int32_t*>(ws + cand_bytes + ls_bytes + li_bytes + gt_bytes + qs_bytes + pr_bytes);
+    dense_overflow_check_kernel<<<nq, 256, 0, stream>>>(kp.list_scores, kp.list_ids, ranges, nq, k_list, k, out_scores,
+                                                        out_ids, k_out, flags);
+    e = cudaGetLastError();
+    std::vector<int32_t> hf((size_t)nq);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hf.data(), flags, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // the one host decision of this path
+    if (e != cudaSuccess) {
+      *err = cudaGetErrorString(e);
+      return -3;
+    }
+    *launched = 3;
+    for (int q = 0; q < nq; ++q)
+      if (hf[(size_t)q]) redo->push_back(q);
+  }
   return 0;
 }
 

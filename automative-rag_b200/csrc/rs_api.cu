@@ -34,6 +34,7 @@ struct rs_handle {
   int64_t gmap_n = -1;
   int32_t gmap_d = -1;
   bool gmap_ok = false;
+  int last_dense_redo = 0;  // queries the last batched k > 128 call re-ran through the scan
   bool has_last = false;
   cudaEvent_t order_ev = nullptr;
   // dense scan workspace
@@ -302,6 +303,7 @@ int rs_last_call_stats(rs_handle* h, rs_call_stats* out) {
   return RS_OK;
 }
 int rs_last_dense_impl(const rs_handle* h) { return h ? h->last_dense_impl : 0; }
+int rs_last_dense_redo(const rs_handle* h) { return h ? h->last_dense_redo : 0; }
 int rs_last_maxsim_impl(const rs_handle* h) { return h ? h->last_maxsim_impl : 0; }
 
 // ------------------------------------------------------------------------------ dense
@@ -329,43 +331,12 @@ int rs_dense_topk(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_
   ProfScope prof(h, st);
   const int64_t scan_bytes = n * (int64_t)d * 2;
 
-  int impl = h->dense_impl;
-  if (impl == RS_DENSE_AUTO)
-    impl = rs::tc5_dense_supported(h->tc5, n, d, nq, k, mask, mask_stride_words, /*worthwhile=*/true) ? RS_DENSE_TCGEN05 : RS_DENSE_SCAN;
-  if (impl == RS_DENSE_TCGEN05) {
-    if (!rs::tc5_dense_supported(h->tc5, n, d, nq, k, mask, mask_stride_words))
-      return fail(h, RS_ERR_UNSUPPORTED, "rs_dense_topk: tcgen05 batched path needs nq >= 2, n >= 256, d %% 64 == 0, k <= 128");
-    int launched = 0;
-    std::string err;
-    int rc = rs::tc5_dense_topk(h->tc5, corpus, n, d, dtype, inv_norm, metric, queries, nq, mask, mask_stride_words, k, id_base, out_scores,
-                                out_ids, st, &launched, &err);
-    h->launches += launched;
-    h->last_dense_impl = RS_DENSE_TCGEN05;
-    if (rc != RS_OK) return fail(h, rc, "rs_dense_topk(tcgen05): %s", err.c_str());
-    prof.finish(RS_CALL_DENSE_TOPK, RS_DENSE_TCGEN05, nq, scan_bytes, 2.0 * nq * (double)n * d);
-    return RS_OK;
-  }
-
-  h->last_dense_impl = RS_DENSE_SCAN;
-  const size_t elt = 2;
-  // Filtered scans fetch the passing rows of sparse mask words four per TMA instruction (tile::gather4) through a
-  // row tensor map of the corpus; encoded on the host (~1 us) when the corpus changes, kept in the handle.
+  // one single-query scan launch (query qi of the call); `chained`: it is one of several launches of this call
   const CUtensorMap* gather_map = nullptr;
-  static const bool no_gather4 = getenv("RS_SCAN_NO_GATHER4") != nullptr;
-  if (mask != nullptr && n > 0 && !no_gather4 && rs::scan_gather4_supported(d)) {
-    if (h->gmap_corpus != corpus || h->gmap_n != n || h->gmap_d != d) {
-      std::string err;
-      h->gmap_ok = rs::tc5_encode_rows(h->tc5, &h->gmap, corpus, (uint64_t)n, (uint32_t)d * 2u, &err);
-      h->gmap_corpus = corpus;
-      h->gmap_n = n;
-      h->gmap_d = d;
-    }
-    if (h->gmap_ok) gather_map = &h->gmap;
-  }
-  for (int qi = 0; qi < nq; ++qi) {
+  auto scan_one = [&](int qi, bool pdl, bool chained) -> int {
     rs::ScanParams p{};
     p.corpus = corpus;
-    p.query = static_cast<const uint8_t*>(queries) + (size_t)qi * d * elt;
+    p.query = static_cast<const uint8_t*>(queries) + (size_t)qi * d * 2;
     p.inv_norm = (metric == RS_METRIC_COSINE) ? inv_norm : nullptr;
     p.mask = mask ? mask + (size_t)qi * mask_stride_words : nullptr;
     p.n = n;
@@ -381,9 +352,62 @@ int rs_dense_topk(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_
     p.out_ids = out_ids + (size_t)qi * k;
     const int ctr = (int)((h->scan_seq - 1) & (kScanCounters - 1));
     p.unit_counter = h->unit_ctr + ctr;
-    cudaError_t e = rs::launch_dense_scan(p, dtype, h->num_sms, /*pdl=*/qi > 0, st, gather_map, /*chained=*/nq > 1);
+    cudaError_t e = rs::launch_dense_scan(p, dtype, h->num_sms, pdl, st, gather_map, chained);
     if (e != cudaSuccess) return cuda_fail(h, e, "dense_scan_kernel launch");
     h->launches += 1;
+    return RS_OK;
+  };
+  // Filtered scans fetch the passing rows of sparse mask words four per TMA instruction (tile::gather4) through a
+  // row tensor map of the corpus; encoded on the host (~1 us) when the corpus changes, kept in the handle.
+  auto prepare_gather_map = [&]() {
+    static const bool no_gather4 = getenv("RS_SCAN_NO_GATHER4") != nullptr;
+    if (mask != nullptr && n > 0 && !no_gather4 && rs::scan_gather4_supported(d)) {
+      if (h->gmap_corpus != corpus || h->gmap_n != n || h->gmap_d != d) {
+        std::string err;
+        h->gmap_ok = rs::tc5_encode_rows(h->tc5, &h->gmap, corpus, (uint64_t)n, (uint32_t)d * 2u, &err);
+        h->gmap_corpus = corpus;
+        h->gmap_n = n;
+        h->gmap_d = d;
+      }
+      if (h->gmap_ok) gather_map = &h->gmap;
+    }
+  };
+
+  int impl = h->dense_impl;
+  if (impl == RS_DENSE_AUTO)
+    impl = rs::tc5_dense_supported(h->tc5, n, d, nq, k, mask, mask_stride_words, /*worthwhile=*/true) ? RS_DENSE_TCGEN05 : RS_DENSE_SCAN;
+  if (impl == RS_DENSE_TCGEN05) {
+    if (!rs::tc5_dense_supported(h->tc5, n, d, nq, k, mask, mask_stride_words))
+      return fail(h, RS_ERR_UNSUPPORTED,
+                  "rs_dense_topk: tcgen05 batched path needs nq >= 2, n >= 256, d %% 64 == 0, k <= 128 (k <= 1024 when the "
+                  "corpus ranges can hold twice their share of the answer)");
+    int launched = 0;
+    std::string err;
+    std::vector<int> redo;
+    int rc = rs::tc5_dense_topk(h->tc5, corpus, n, d, dtype, inv_norm, metric, queries, nq, mask, mask_stride_words, k, id_base, out_scores,
+                                out_ids, st, &launched, &err, &redo);
+    h->launches += launched;
+    h->last_dense_impl = RS_DENSE_TCGEN05;
+    if (rc != RS_OK) return fail(h, rc, "rs_dense_topk(tcgen05): %s", err.c_str());
+    // k > 128: queries for which a corpus range may have held more of the answer than its list keeps are re-run
+    // through the exact single-query scan (dense_tc5.cu, dense_overflow_check_kernel)
+    h->last_dense_redo = (int)redo.size();
+    if (!redo.empty()) {
+      prepare_gather_map();
+      for (size_t i = 0; i < redo.size(); ++i) {
+        rc = scan_one(redo[i], /*pdl=*/i > 0, /*chained=*/redo.size() > 1);
+        if (rc != RS_OK) return rc;
+      }
+    }
+    prof.finish(RS_CALL_DENSE_TOPK, RS_DENSE_TCGEN05, nq, scan_bytes, 2.0 * nq * (double)n * d);
+    return RS_OK;
+  }
+
+  h->last_dense_impl = RS_DENSE_SCAN;
+  prepare_gather_map();
+  for (int qi = 0; qi < nq; ++qi) {
+    int rc = scan_one(qi, /*pdl=*/qi > 0, /*chained=*/nq > 1);
+    if (rc != RS_OK) return rc;
   }
   prof.finish(RS_CALL_DENSE_TOPK, RS_DENSE_SCAN, nq, scan_bytes * nq, 2.0 * nq * (double)n * d);
   return RS_OK;

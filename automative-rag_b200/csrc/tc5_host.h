@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "kernels.h"
 
@@ -39,6 +40,10 @@ bool tc5_dense_supported(const Tc5State* s, int64_t n, int d, int nq, int k, con
                          int64_t mask_stride_words, bool worthwhile = false);
 int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype, const float* inv_norm, int metric,
                    const void* queries, int nq, const uint32_t* mask, int64_t mask_stride_words, int k, int64_t id_base, float* out_scores,
-                   int64_t* out_ids, cudaStream_t stream, int* launched, std::string* err);
+                   int64_t* out_ids, cudaStream_t stream, int* launched, std::string* err,
+                   std::vector<int>* redo = nullptr);
+// k <= 128: one pass, nothing to redo.  128 < k <= 1024: every corpus range keeps its best <= 128 rows, the merge takes
+// the k best of all ranges' lists, and `redo` receives the queries for which a range may have held more of the answer
+// than it could keep (the call synchronises the stream to learn that); the caller re-runs those through the scan.
 
 }  // namespace rs

@@ -979,6 +979,54 @@ def extra_config5(cx):
         res["parity_detail"] = {**detail, "queries_checked": npq, "seconds": round(time.perf_counter() - t0, 1),
                                 "protocol": "SURVEY §8d (i)-(iii) + oracle MaxSim/rerank of the winners; CPU numpy / torch-CPU"}
 
+    # ---- the same pipeline with the step's queries TOGETHER (stage 1 is "tensor for large B"):
+    # ONE batched tcgen05 pass over the shard for all queries — k1 = 1000 through the two-level lists of dense_tc5.cu —
+    # one exchange, ONE candidate-MaxSim launch, one max-exchange, one rerank tail.  Checked against the per-query path:
+    # stage-1 id lists may differ only in entries tied with the k1-th score, the top-10 must be identical whenever the
+    # stage-1 lists are.
+    def batch_all():
+        s1, ids = index.search(queries_d, k1)
+        slot = torch.where(ids >= 0, ids % P, torch.full_like(ids, -1)).to(torch.int32)
+        sc = rerank.scores(qtok, slot)
+        top_idx, top_sc = eng.rerank_postprocess(sc, None, k2)
+        return torch.gather(ids, 1, top_idx.long()), top_sc, ids, s1
+
+    try:
+        eng.set_dense_impl(_ffi.RS_DENSE_AUTO)
+        ms_batch = cx.timed(batch_all, 2, warm=1)
+        impl_b, redo_b = eng.last_dense_impl, eng.last_dense_redo
+        ms_stage1_b = cx.timed(lambda: eng.dense_topk(corpus, queries_d, k1, id_base=lo), 2, warm=0)
+        top_b, tsc_b, ids_b, s1_b = [t.clone() for t in batch_all()]
+        eng.set_dense_impl(_ffi.RS_DENSE_SCAN)
+        ok_b, same_lists, same_top = True, 0, 0
+        for j in range(nqs):
+            top_j, _, ids_j, s1_j, _ = [t.clone() for t in one_query(j)]
+            kth = float(s1_j[k1 - 1])
+            extra = ~torch.isin(ids_b[j], ids_j)
+            if bool(extra.any()):
+                ok_b &= bool(((s1_b[j][extra] - kth).abs() <= 1e-3 * abs(kth) + 1e-6).all())
+            else:
+                same_lists += 1
+                ok_b &= bool(torch.equal(top_j, top_b[j]))
+            same_top += int(torch.equal(top_j, top_b[j]))
+        batch_bytes = n_local * D * 2
+        res["batched"] = {
+            "queries_per_batch": nqs, "ms_per_batch": ms_batch, "queries_per_s": nqs * 1e3 / ms_batch, "stage1_ms": ms_stage1_b,
+            "stage1_kernel": "dense_tc5_kernel (k1 = 1000 via per-range lists of <= 128 + exactness check)"
+                             if impl_b == _ffi.RS_DENSE_TCGEN05 else "dense_scan_kernel loop",
+            "queries_rerun_through_scan": redo_b,
+            "roofline": {"bound": "hbm", "achieved": batch_bytes / ms_batch / 1e6, "peak": cx.hbm_peak, "unit": "GB/s per GPU",
+                         "frac": batch_bytes / ms_batch / 1e6 / cx.hbm_peak, "traffic": None, "peak_source": cx.peak_src,
+                         "note": "whole batch (one pass over the shard for all queries + exchanges + MaxSim + top-10) "
+                                 "against the bytes of ONE pass over the shard"},
+            "parity_vs_per_query_path": {"ok": cx.all_ok(ok_b), "identical_stage1_lists": same_lists, "identical_top10": same_top,
+                                         "queries": nqs},
+        }
+    except Exception as e:  # noqa: BLE001
+        res["batched"] = {"error": str(e)[:300]}
+    finally:
+        eng.set_dense_impl(_ffi.RS_DENSE_SCAN)
+
     # ---- the same scan strong-scaled: 12.5M rows in total, every rank scans the first 12.5M / G rows of its shard
     n_strong = n_local // world
     strong = ShardedDenseIndex(corpus[:n_strong], rank * n_strong, engine=eng, metric=_ffi.RS_METRIC_COSINE)

@@ -132,6 +132,8 @@ int rs_scan_plan(int32_t d, int32_t k, int64_t* out7);
 int rs_scan_plan_chained(int32_t d, int32_t k, int64_t* out8);
 /* Family used by the most recent rs_dense_topk / rs_maxsim call on this handle. */
 int rs_last_dense_impl(const rs_handle* h);
+/* Queries the most recent batched rs_dense_topk call with k > 128 re-ran through the single-query scan (usually 0). */
+int rs_last_dense_redo(const rs_handle* h);
 int rs_last_maxsim_impl(const rs_handle* h);
 
 /*
@@ -167,6 +169,11 @@ int rs_last_call_stats(rs_handle* h, rs_call_stats* out);
  *   id_base     added to the local row index to form the returned id (shard offset)
  *   out_scores  [nq, k] fp32, descending; -inf where fewer than k rows pass
  *   out_ids     [nq, k] int64;  -1 where fewer than k rows pass
+ *
+ * Kernel families (rs_set_dense_impl; AUTO picks): a single-query scan launch per query (any k), or — from two
+ * queries on — ONE batched tcgen05 pass for the whole call: k <= 128 directly; 128 < k <= 1024 with every corpus
+ * range keeping its best <= 128 rows and an exactness check afterwards, in which case the call synchronises the
+ * stream once and re-runs through the scan the queries whose answer a range could not hold (rs_last_dense_redo).
  */
 int rs_dense_topk(rs_handle* h, const void* corpus, int64_t n, int32_t d, int32_t dtype,
                   const float* inv_norm, int32_t metric, const void* queries, int32_t nq,

@@ -242,3 +242,56 @@ def test_batched_first_tile_threshold_with_sparse_filter(engine, passing_in_firs
     mask = torch.from_numpy(odense.pack_mask(bits).view(np.int32).copy()).to(engine.device)
     s, i = _run(engine, c, q, k, _ffi.RS_DENSE_TCGEN05, mask=mask)
     _check_all(s, i, c, q, k, bits)
+
+
+# ---------------------------------------------------------------------------------- 128 < k <= 1024: two-level lists
+@pytest.mark.parametrize("n,d,nq,k,p", [(200_000, 128, 16, 1000, 1.0), (60_000, 1024, 300, 500, 1.0),
+                                        (300_000, 64, 5, 1024, 0.5), (150_000, 256, 130, 129, 1.0),
+                                        (90_000, 128, 2, 300, 0.2)])
+def test_batched_long_lists_match_oracle(engine, n, d, nq, k, p):
+    """k up to 1024 in ONE batched pass (config 5's stage 1 with k1 = 1000, `tests/test_retrieval.py:206-258` with a large
+    retrieval_k): every corpus range keeps its best <= 128 rows, the merge takes the k best of all lists; on random data
+    no range holds more of the answer than it can keep, so nothing is re-run."""
+    c, q = _case(n + k, n, d, nq, torch.bfloat16)
+    bits = None if p == 1.0 else bernoulli_mask(k, n, p)
+    kw = {}
+    if bits is not None:
+        kw["mask"] = torch.from_numpy(odense.pack_mask(bits).view(np.int32).copy()).to(engine.device)
+    s, i = _run(engine, c, q, k, _ffi.RS_DENSE_TCGEN05, **kw)
+    assert engine.last_dense_redo == 0
+    _check_all(s, i, c, q, k, bits)
+
+
+def test_batched_long_lists_redo_when_a_range_overflows(engine):
+    """The exactness check of the two-level lists: (a) the whole answer sits in ONE 256-row tile (one range, which keeps
+    at most 128 rows), (b) thousands of exactly tied top scores.  Both must be detected and re-run through the
+    single-query scan, and the result must equal the oracle's (ties in ascending id)."""
+    n, d, nq, k = 100_000, 128, 6, 200
+    c, q = _case(91, n, d, nq, torch.float16)
+    c = c * 0.1                                            # background rows score low
+    qn = (q[0].float() / q[0].float().norm())
+    for r in range(256):                                   # rows 0..255 (tile 0): distinct high scores for query 0
+        c[r] = (qn * (1.0 - r * 1e-3)).half()
+    s, i = _run(engine, c, q, k, _ffi.RS_DENSE_TCGEN05)
+    assert engine.last_dense_redo >= 1
+    _check_all(s, i, c, q, k)
+    assert i[0].tolist() == list(range(k))
+    # (b) 3000 copies of one row: an exactly tied top block larger than k
+    c2, q2 = _case(92, 50_000, 128, 4, torch.float16)
+    c2[1000:4000] = (q2[1].float() / q2[1].float().norm()).half()
+    s, i = _run(engine, c2, q2, 300, _ffi.RS_DENSE_TCGEN05)
+    assert engine.last_dense_redo >= 1
+    _check_all(s, i, c2, q2, 300)
+    assert i[1].tolist() == list(range(1000, 1300))
+
+
+def test_auto_takes_long_lists_to_the_batched_kernel(engine):
+    n, d, nq, k = 250_000, 128, 8, 1000
+    c, q = _case(93, n, d, nq, torch.float16)
+    engine.set_dense_impl(_ffi.RS_DENSE_AUTO)
+    s, i = engine.dense_topk(c.to(engine.device), q.to(engine.device), k)
+    torch.cuda.synchronize()
+    assert engine.last_dense_impl == _ffi.RS_DENSE_TCGEN05
+    _check_all(s.cpu().numpy(), i.cpu().numpy(), c, q, k)
+    s2, i2 = _run(engine, c, q, k, _ffi.RS_DENSE_SCAN)
+    assert (i2 == i.cpu().numpy()).mean() > 0.99            # ids equal the scan's except near-ties
