@@ -48,6 +48,8 @@ constexpr int kDtBN = 256;        // corpus rows per tile (UMMA N)
 constexpr int kDtBK = 64;         // K elements per stage (one 128-byte swizzle row)
 constexpr int kDtMT = 2;          // 128-query UMMA tiles per CTA (single-CTA tiles) / CTAs per pair
 constexpr int kDtStages = 3;
+constexpr int kDtStagesSmall = 4;  // batches of <= 128 queries stage ONE query tile: 48 KB stages, four of them (128 KB of
+                                   // corpus in flight per SM instead of 96: the pass is HBM-bound, not tensor-bound)
 constexpr int kDtStagesPair = 6;  // a pair's stage is half the size: 128 query rows + 128 corpus rows per CTA
 constexpr int kDtMaxGroups = 16;  // groups of ranges behind the cross-range bound (one batch of loads per refresh)
 constexpr int kDtMaxGm = 8;       // best scores tracked per (range, query) for the cross-range bound
@@ -119,13 +121,16 @@ __device__ __forceinline__ void warp_sort_desc(uint64_t* keys, int n, int lane) 
 //   operand bytes per flop.  The leader (cluster rank 0) issues the MMAs; TMA loads of both CTAs count on the leader's
 //   barrier; tcgen05.commit multicasts "stage free" / "accumulator ready" to both; the peer's epilogue hands
 //   accumulators back with a remote mbarrier arrive.
-template <bool BF16, bool PAIR>
+// SMALL (single-CTA tiles only): the batch fits one 128-query tile, so a stage holds one A tile and the ring is a
+//   stage deeper.
+template <bool BF16, bool PAIR, bool SMALL>
 __global__ void __launch_bounds__(kDtThreads, 1)
     dense_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
                      const DenseTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr int kStages = PAIR ? kDtStagesPair : kDtStages;
-  constexpr int kMT = PAIR ? 1 : kDtMT;                       // 128-query tiles staged by this CTA
+  static_assert(!(PAIR && SMALL), "SMALL is a single-CTA variant");
+  constexpr int kStages = PAIR ? kDtStagesPair : (SMALL ? kDtStagesSmall : kDtStages);
+  constexpr int kMT = (PAIR || SMALL) ? 1 : kDtMT;            // 128-query tiles staged by this CTA
   constexpr uint32_t kBRows = PAIR ? kDtBN / 2 : kDtBN;       // corpus rows staged by this CTA
   constexpr uint32_t kBBytes = kBRows * 128;
   constexpr uint32_t kStageBytes = kMT * kDtABytes + kBBytes;
@@ -141,7 +146,7 @@ __global__ void __launch_bounds__(kDtThreads, 1)
   const int ntiles = (p.tiles_total - range + p.num_ranges - 1) / p.num_ranges;
   const int q0 = mgroup * (kDtMT * 128) + (PAIR ? (int)rank * 128 : 0);
   // active 128-query tiles: a pair always runs its one M = 256 MMA (rows past nq are TMA zero fill)
-  const int n_act = PAIR ? 1 : min(kDtMT, (p.nq - q0 + 127) / 128);
+  const int n_act = PAIR ? 1 : min(kMT, (p.nq - q0 + 127) / 128);
   const int kblocks = p.d / kDtBK;
   // Two accumulator generations (the epilogue of tile t overlaps the MMAs of tile t+1) whenever a generation needs
   // only 256 TMEM columns: always for pairs, and for single-CTA tiles when just one 128-query tile is active.
@@ -873,8 +878,11 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
     cudaMemsetAsync(trace_dev, 0, (size_t)1024 * 16 * sizeof(long long), stream);
     kp.trace = n_ctas <= 1024 ? trace_dev : nullptr;
   }
-  const size_t stage_bytes = pair ? (size_t)(kDtABytes + kDtBBytes / 2) : (size_t)kDtStageBytes;
-  const size_t smem = 1024 + (size_t)(pair ? kDtStagesPair : kDtStages) * stage_bytes +
+  static const int no_small = getenv("RS_DENSE_NO_SMALL") ? 1 : 0;  // A/B switch
+  const bool small = !pair && nq <= 128 && !no_small;
+  const size_t stage_bytes = pair ? (size_t)(kDtABytes + kDtBBytes / 2)
+                                  : (small ? (size_t)(kDtABytes + kDtBBytes) : (size_t)kDtStageBytes);
+  const size_t smem = 1024 + (size_t)(pair ? kDtStagesPair : (small ? kDtStagesSmall : kDtStages)) * stage_bytes +
                       (size_t)(pair ? 4 : 8) * kDtCap * sizeof(uint64_t) + 256;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = pair ? dim3(2 * ranges, mgroups) : dim3(ranges, mgroups);
@@ -889,15 +897,15 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
   cfg.attrs = attr;
   cfg.numAttrs = pair ? 1 : 0;
   cudaError_t e;
-#define RS_DT_LAUNCH(BF, PR)                                                                                        \
+#define RS_DT_LAUNCH(BF, PR, SM)                                                                                    \
   {                                                                                                                 \
-    e = cudaFuncSetAttribute(dense_tc5_kernel<BF, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
-    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, dense_tc5_kernel<BF, PR>, map_q, map_c, kp);                 \
+    e = cudaFuncSetAttribute(dense_tc5_kernel<BF, PR, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, dense_tc5_kernel<BF, PR, SM>, map_q, map_c, kp);             \
   }
   if (dtype == 1) {
-    if (pair) RS_DT_LAUNCH(true, true) else RS_DT_LAUNCH(true, false)
+    if (pair) RS_DT_LAUNCH(true, true, false) else if (small) RS_DT_LAUNCH(true, false, true) else RS_DT_LAUNCH(true, false, false)
   } else {
-    if (pair) RS_DT_LAUNCH(false, true) else RS_DT_LAUNCH(false, false)
+    if (pair) RS_DT_LAUNCH(false, true, false) else if (small) RS_DT_LAUNCH(false, false, true) else RS_DT_LAUNCH(false, false, false)
   }
 #undef RS_DT_LAUNCH
   if (e != cudaSuccess) {

@@ -197,7 +197,7 @@ def test_sass_of_the_hot_kernels_uses_the_blackwell_units():
         assert "UTMALDG" in sass and "UTCHMMA" in sass and "LDTM" in sass, k
     pair = [s for k, s in kernels("dense_tc5_kernel").items() if "UTCHMMA.2CTA" in s]
     single = [s for k, s in kernels("dense_tc5_kernel").items() if "UTCHMMA.2CTA" not in s]
-    assert len(pair) == 2 and len(single) == 2                                   # fp16 / bf16 x pair / single-CTA
+    assert len(pair) == 2 and len(single) == 4                                   # fp16 / bf16 x pair / single-CTA (two tiles, one tile + deeper ring)
     for sass in pair:
         assert "UTMALDG.2D.2CTA" in sass and "UTCBAR.2CTA.MULTICAST" in sass and "UCGABAR" in sass
         assert sass.count("MEMBAR.ALL.GPU") <= 2
