@@ -564,14 +564,17 @@ __global__ void __launch_bounds__(kDtThreads, 1)
         if (gm > 0 && t == next_refresh) {
           // The bound moves like 1/rows_seen: refresh after every tile at first, then at geometrically growing
           // distances.
-          next_refresh = t + 1 + t / 8;
+          // (more than 16 groups — the long lists of k > 128 — cost one round trip per 16 words: refresh half as often)
+          next_refresh = t + 1 + t / 8 + (p.cross_groups > kDtMaxGroups ? 1 + t / 8 : 0);
           const long long tr0 = tracing ? clock64() : 0;
           uint32_t lo = 0xFFFFFFFFu;
           const uint32_t* g = p.gthr + (valid ? query : 0);
+          for (int j0 = 0; j0 < p.cross_groups; j0 += kDtMaxGroups) {
 #pragma unroll
-          for (int j = 0; j < kDtMaxGroups; ++j) {  // one L2 round trip: the loads are independent
-            const uint32_t v = j < p.cross_groups ? __ldcg(g + (size_t)j * p.nq) : 0xFFFFFFFFu;
-            lo = min(lo, v);
+            for (int j = 0; j < kDtMaxGroups; ++j) {  // one L2 round trip: the loads are independent
+              const uint32_t v = j0 + j < p.cross_groups ? __ldcg(g + (size_t)(j0 + j) * p.nq) : 0xFFFFFFFFu;
+              lo = min(lo, v);
+            }
           }
           if (valid && lo > 1u) {  // every group has a published value: the float just below T
             thr_cross = orderable_f32(lo - 1u);
@@ -858,11 +861,16 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
   }
   static const int cross_off = getenv("RS_DENSE_NO_CROSS_THR") ? 1 : 0;  // A/B switch for scripts/batch_bench.py
   const int gm = std::max((k + ranges - 1) / ranges, (k + kDtMaxGroups - 1) / kDtMaxGroups);
-  // two-level lists: the cross-range bound would vouch for k_run rows, not for the k_out the caller wants — off
   kp.gm = (ranges > 1 && gm <= kDtMaxGm && !cross_off && !pl.two_level) ? gm : 0;
+  // two-level lists: the bound must vouch for the k_out rows the caller wants, not for the k_run a range keeps: every
+  // range publishes its 8th best and the ranges form ceil(k_out / 8) groups — possible while that is <= ranges (the
+  // 148 ranges of a batch of <= 128 queries: k_out <= 1184).  Without it a range's own k_run-th best is the only
+  // threshold and 80 % of the 32-row chunks of a 16-query batch take the append path (trace: epilogue 71 % in appends
+  // and compactions, the MMA warp waiting 30 % for accumulators).
+  if (pl.two_level && ranges > 1 && !cross_off && (k_out + kDtMaxGm - 1) / kDtMaxGm <= ranges) kp.gm = kDtMaxGm;
   static const int bootstrap_off = getenv("RS_DENSE_NO_BOOTSTRAP") ? 1 : 0;
   kp.bootstrap = bootstrap_off ? 0 : 1;
-  kp.cross_groups = kp.gm > 0 ? std::min(ranges, (k + kp.gm - 1) / kp.gm) : 1;
+  kp.cross_groups = kp.gm > 0 ? std::min(ranges, ((pl.two_level ? k_out : k) + kp.gm - 1) / kp.gm) : 1;
   if (kp.gm > 0) {
     cudaError_t me = cudaMemsetAsync(kp.gthr, 0, gt_bytes, stream);
     if (me != cudaSuccess) {
