@@ -860,8 +860,15 @@ int tc5_dense_topk(Tc5State* s, const void* corpus, int64_t n, int d, int dtype,
     }
   }
   static const int cross_off = getenv("RS_DENSE_NO_CROSS_THR") ? 1 : 0;  // A/B switch for scripts/batch_bench.py
-  const int gm = std::max((k + ranges - 1) / ranges, (k + kDtMaxGroups - 1) / kDtMaxGroups);
+  // Rows a range vouches for: as few as the number of ranges allows, down to 64 groups.  The first version capped the
+  // groups at 16 (one batch of loads per refresh), which made a range vouch for 7 rows at k = 100 — its 7th best is
+  // far below the global 100th; with the refresh reading 16 words per round trip, 50 groups of 2 rows take 64 / 128
+  // queries x 1M rows at k = 100 from 0.64 / 0.68 to 0.43 / 0.46 ms (profiles/r02_dense_gm_ab.txt).
+  constexpr int kGroupCap = 64;
+  const int gm = std::max((k + ranges - 1) / ranges, (k + std::min(ranges, kGroupCap) - 1) / std::min(ranges, kGroupCap));
   kp.gm = (ranges > 1 && gm <= kDtMaxGm && !cross_off && !pl.two_level) ? gm : 0;
+  static const int gm_env = getenv("RS_DENSE_GM") ? atoi(getenv("RS_DENSE_GM")) : 0;  // experiment: rows a range vouches for
+  if (gm_env > 0 && kp.gm > 0 && !pl.two_level && gm_env <= kDtMaxGm && (k + gm_env - 1) / gm_env <= ranges) kp.gm = gm_env;
   // two-level lists: the bound must vouch for the k_out rows the caller wants, not for the k_run a range keeps: every
   // range publishes its 8th best and the ranges form ceil(k_out / 8) groups — possible while that is <= ranges (the
   // 148 ranges of a batch of <= 128 queries: k_out <= 1184).  Without it a range's own k_run-th best is the only
