@@ -28,7 +28,9 @@ while time.time() - t0 < budget:
     p = float(rng.choice([1.0, 1.0, 0.9, 0.5, 0.05, 0.0]))
     bits = None if p == 1.0 else (rng.random(n) < p)
     mask = None if bits is None else torch.from_numpy(pack_bits(bits)).to(dev)
-    impl = _ffi.RS_DENSE_TCGEN05 if (nq >= 2 and n >= 256 and k <= 128 and rng.random() < 0.7) else _ffi.RS_DENSE_SCAN
+    # the batched kernel: k <= 128 directly, k = 1000 through the per-range lists (needs enough corpus ranges)
+    batched_ok = nq >= 2 and n >= 256 and (k <= 128 or n >= 65_537)
+    impl = _ffi.RS_DENSE_TCGEN05 if (batched_ok and rng.random() < 0.7) else _ffi.RS_DENSE_SCAN
     eng.set_dense_impl(impl)
     s, i = eng.dense_topk(c, q, k, mask=mask, metric=_ffi.RS_METRIC_IP)
     launches += nq if impl == _ffi.RS_DENSE_SCAN else 2

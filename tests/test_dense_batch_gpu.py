@@ -295,3 +295,20 @@ def test_auto_takes_long_lists_to_the_batched_kernel(engine):
     _check_all(s.cpu().numpy(), i.cpu().numpy(), c, q, k)
     s2, i2 = _run(engine, c, q, k, _ffi.RS_DENSE_SCAN)
     assert (i2 == i.cpu().numpy()).mean() > 0.99            # ids equal the scan's except near-ties
+
+
+def test_batched_long_lists_per_query_masks_ip_inv_norm_id_base(engine):
+    """The long-list path with everything else the entry point takes: a filter per query, inner product with and
+    without inv_norm, an id offset (the shard offset of `ShardedDenseIndex`)."""
+    n, d, nq, k = 120_000, 128, 9, 400
+    c, q = _case(95, n, d, nq, torch.bfloat16, normalise=False)
+    bits = np.stack([bernoulli_mask(100 + j, n, 0.25 + 0.05 * j) for j in range(nq)])
+    mask = torch.stack([torch.from_numpy(odense.pack_mask(b).view(np.int32).copy()) for b in bits]).to(engine.device)
+    s, i = _run(engine, c, q, k, _ffi.RS_DENSE_TCGEN05, mask=mask, metric=_ffi.RS_METRIC_IP, id_base=7_000_000_000)
+    cf, qf = c.float().numpy(), q.float().numpy()
+    for j in range(nq):
+        assert_topk_matches(s[j], i[j], odense.scores_f32(cf, qf[j], _ffi.RS_METRIC_IP), bits[j], k, id_base=7_000_000_000)
+    inv = (1.0 / np.linalg.norm(cf, axis=1)).astype(np.float32)
+    s, i = _run(engine, c, q, k, _ffi.RS_DENSE_TCGEN05, mask=mask, inv_norm=torch.from_numpy(inv).to(engine.device))
+    for j in range(nq):
+        assert_topk_matches(s[j], i[j], odense.scores_f32(cf, qf[j], _ffi.RS_METRIC_COSINE, inv), bits[j], k)
