@@ -9,6 +9,10 @@
 #include <string>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -20,6 +24,72 @@
 namespace {
 thread_local std::string g_create_error;
 }
+
+// Worker threads that stage a host-resident document list into pinned memory (rs_maxsim_list).  They live as long as
+// the handle: creating threads per call and binding each to the device cost ~0.1 ms of a 0.7 ms call, and made six
+// threads slower than three.  A worker spins on the job counter for a short while after a job (the next rerank call
+// usually follows at once) and then parks on a condition variable.
+class StagePool {
+ public:
+  StagePool(int workers, int device) : n_(workers) {
+    for (int w = 0; w < workers; ++w) threads_.emplace_back([this, w, device] { loop(w, device); });
+  }
+  ~StagePool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+      gen_.fetch_add(1);
+    }
+    cv_.notify_all();
+    for (auto& t : threads_) t.join();
+  }
+  int workers() const { return n_; }
+  // runs job(0..workers) — part `workers` on the calling thread — and returns when every part is done
+  void run(const std::function<void(int)>& job) {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      job_ = &job;
+      pending_.store(n_);
+      gen_.fetch_add(1);
+    }
+    cv_.notify_all();
+    job(n_);
+    while (pending_.load(std::memory_order_acquire) != 0) std::this_thread::yield();
+  }
+
+ private:
+  void loop(int w, int device) {
+    cudaSetDevice(device);
+    uint64_t seen = 0;
+    for (;;) {
+      // hot phase: the next job usually arrives within microseconds of the last
+      const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(300);
+      while (gen_.load(std::memory_order_acquire) == seen && std::chrono::steady_clock::now() < until) {
+      }
+      if (gen_.load(std::memory_order_acquire) == seen) {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return gen_.load() != seen; });
+      }
+      const std::function<void(int)>* job;
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        seen = gen_.load();
+        if (stop_) return;
+        job = job_;
+      }
+      (*job)(w);
+      pending_.fetch_sub(1, std::memory_order_release);
+    }
+  }
+  int n_;
+  std::vector<std::thread> threads_;
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::atomic<uint64_t> gen_{0};
+  std::atomic<int> pending_{0};
+  const std::function<void(int)>* job_ = nullptr;
+  bool stop_ = false;
+};
 
 struct rs_handle {
   int device = 0;
@@ -35,6 +105,7 @@ struct rs_handle {
   int32_t gmap_d = -1;
   bool gmap_ok = false;
   int last_dense_redo = 0;  // queries the last batched k > 128 call re-ran through the scan
+  StagePool* stage_pool = nullptr;  // created by the first rs_maxsim_list call with a large host-resident list
   bool has_last = false;
   cudaEvent_t order_ev = nullptr;
   // dense scan workspace
@@ -229,6 +300,7 @@ int rs_destroy(rs_handle* h) {
   if (!h) return RS_OK;
   DeviceGuard guard(h->device);
   cudaDeviceSynchronize();
+  delete h->stage_pool;
   if (h->tc5) rs::tc5_destroy(h->tc5);
   if (h->comm) rs::comm_destroy(h->comm);
   if (h->shard_scores) cudaFree(h->shard_scores);
@@ -833,18 +905,28 @@ int rs_maxsim_list(rs_handle* h, const void* q, int32_t q_on_host, int32_t lq, i
         }
       }
     };
+    // parts = staging threads incl. the caller.  Threads created per call (round 2, first half): 1 / 3 / 6 threads ->
+    // 0.85 / 0.72 / 1.08 ms per call for 9.2 MB of fp32 documents; the handle's persistent workers: 1 / 3 / 6 / 8 / 12
+    // parts -> 0.84 / 0.47 / 0.49 / 0.50 / 0.54 ms (profiles/r02_config1_staging_pool.txt).
     static const int forced_threads = getenv("RS_LIST_THREADS") ? atoi(getenv("RS_LIST_THREADS")) : 0;
-    const int nthreads = forced_threads > 0 ? std::min(forced_threads, nd)
-                                            : (raw_bytes > (4u << 20) ? 3 : 1);  // measured: 1 / 3 / 6 threads ->
-                                                                                 // 0.85 / 0.72 / 1.08 ms for 9.2 MB
-    if (nthreads == 1) {
+    const int want = forced_threads > 0 ? forced_threads : (raw_bytes > (1u << 20) ? 3 : 1);
+    const int parts = std::max(1, std::min(want, nd));
+    if (parts == 1) {
       copy_range(0, nd, false);
     } else {
-      std::vector<std::thread> pool;
-      for (int t = 1; t < nthreads; ++t)
-        pool.emplace_back(copy_range, (int)((int64_t)nd * t / nthreads), (int)((int64_t)nd * (t + 1) / nthreads), true);
-      copy_range(0, nd / nthreads, false);
-      for (auto& t : pool) t.join();
+      if (h->stage_pool && h->stage_pool->workers() != parts - 1) {
+        delete h->stage_pool;
+        h->stage_pool = nullptr;
+      }
+      if (!h->stage_pool) h->stage_pool = new (std::nothrow) StagePool(parts - 1, device);
+      if (!h->stage_pool) {
+        copy_range(0, nd, false);
+      } else {
+        const std::function<void(int)> job = [&](int part) {
+          copy_range((int)((int64_t)nd * part / parts), (int)((int64_t)nd * (part + 1) / parts), false);
+        };
+        h->stage_pool->run(job);
+      }
     }
     if (copy_err.load() != 0) return cuda_fail(h, (cudaError_t)copy_err.load(), "H2D(document list)");
   }
