@@ -56,6 +56,7 @@ SIGNATURES = {
     "rs_allgather_topk": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P]),
     "rs_allgather": (C.c_int, [_P, _P, _I64, _P, _P]),
     "rs_allreduce_max_f32": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "rs_owned_candidates": (C.c_int, [_P, _P, _I32, _I64, _I32, _I32, _I64, _P, _P]),
     "rs_dense_topk_sharded_host": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _P, _I32, _P, _I64, _I32, _I64, _P, _P, _P]),
 }
 
@@ -424,6 +425,18 @@ class Engine:
         rc = self._lib.rs_allgather(self._h, _ptr(local), local.numel() * local.element_size(), _ptr(out),
                                     _stream_ptr(self.device))
         self._check(rc, "rs_allgather")
+        return out
+
+    def owned_candidates(self, cand: torch.Tensor, world: int, rank: int, pool: int = 0) -> torch.Tensor:
+        """Global candidate ids (int32 / int64, any shape; negative = padding; modulo `pool` first when pool > 0) ->
+        int32 local document indices of THIS rank under round-robin ownership, -1 elsewhere.  One launch."""
+        self._dev(cand, "cand")
+        if cand.dtype not in (torch.int32, torch.int64) or not cand.is_contiguous():
+            raise ValueError("cand must be a contiguous int32 / int64 tensor")
+        out = torch.empty(cand.shape, dtype=torch.int32, device=self.device)
+        rc = self._lib.rs_owned_candidates(self._h, _ptr(cand), 1 if cand.dtype == torch.int64 else 0, cand.numel(),
+                                           world, rank, pool, _ptr(out), _stream_ptr(self.device))
+        self._check(rc, "rs_owned_candidates")
         return out
 
     def allreduce_max(self, local: torch.Tensor) -> torch.Tensor:

@@ -86,6 +86,10 @@ cudaError_t launch_filter_mask(const int32_t* const* cols_dev, int nclauses, con
                                const int32_t* val_offsets_dev, const uint32_t* tombstone, int64_t n,
                                uint32_t* out_mask, int num_sms, cudaStream_t stream);
 
+// global candidate ids -> local document indices of the owning rank (round-robin ownership), -1 elsewhere
+cudaError_t launch_owned_candidates(const void* cand, int is_i64, int64_t n, int world, int rank, int64_t pool,
+                                    int32_t* out, cudaStream_t stream);
+
 // document list -> packed tokens in the compute dtype (ColBERTReranker._compute_maxsim_scores call shape)
 cudaError_t launch_gather_docs(const void* const* ptrs_dev, const uint8_t* staged_dev, const int64_t* src_off_dev,
                                const int32_t* offsets_dev, int nd, int max_len, int d, int src_dtype, int dst_dtype,

@@ -645,6 +645,22 @@ int rs_rerank_postprocess(rs_handle* h, const float* scores, const float* other,
   return RS_OK;
 }
 
+int rs_owned_candidates(rs_handle* h, const void* cand, int32_t cand_is_i64, int64_t n, int32_t world, int32_t rank,
+                        int64_t pool, int32_t* out_local, void* stream) {
+  if (!h) return RS_ERR_INVALID_ARG;
+  if (n < 0 || world < 1 || rank < 0 || rank >= world || pool < 0)
+    return fail(h, RS_ERR_INVALID_ARG, "rs_owned_candidates: bad n / world / rank / pool");
+  if (n == 0) return RS_OK;
+  if (!cand || !out_local) return fail(h, RS_ERR_INVALID_ARG, "rs_owned_candidates: NULL argument");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  order_after_last(h, st);
+  cudaError_t e = rs::launch_owned_candidates(cand, cand_is_i64, n, world, rank, pool, out_local, st);
+  if (e != cudaSuccess) return cuda_fail(h, e, "owned_candidates_kernel launch");
+  h->launches += 1;
+  return RS_OK;
+}
+
 int rs_filter_mask(rs_handle* h, const int32_t* const* cols, int32_t nclauses, const int32_t* values,
                    const int32_t* val_offsets, const uint32_t* tombstone, int64_t n, uint32_t* out_mask, void* stream) {
   if (!h) return RS_ERR_INVALID_ARG;

@@ -191,6 +191,31 @@ __global__ void __launch_bounds__(256) filter_mask_kernel(FilterClauses fc, int 
   }
 }
 
+// ------------------------------------------------------------------------- candidate ownership (sharded MaxSim)
+// Documents are owned round-robin (owner = id % world, local index = id / world): global candidate ids -> this
+// rank's local document indices, -1 for candidates another rank owns and for padding (an index outside the collection
+// is an empty document the MaxSim kernels skip and score -inf).  One launch instead of six element-wise torch ops.
+template <typename T>
+__global__ void owned_candidates_kernel(const T* __restrict__ cand, int64_t n, int world, int rank, int64_t pool,
+                                        int32_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t id = (int64_t)cand[i];
+  if (id >= 0 && pool > 0) id %= pool;  // config 5: document slot = row id mod pool size
+  out[i] = (id >= 0 && id % world == rank) ? (int32_t)(id / world) : -1;
+}
+
+cudaError_t launch_owned_candidates(const void* cand, int is_i64, int64_t n, int world, int rank, int64_t pool,
+                                    int32_t* out, cudaStream_t stream) {
+  const int threads = 256;
+  const int blocks = (int)((n + threads - 1) / threads);
+  if (is_i64)
+    owned_candidates_kernel<int64_t><<<blocks, threads, 0, stream>>>(static_cast<const int64_t*>(cand), n, world, rank, pool, out);
+  else
+    owned_candidates_kernel<int32_t><<<blocks, threads, 0, stream>>>(static_cast<const int32_t*>(cand), n, world, rank, pool, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_filter_mask(const int32_t* const* cols_host, int nclauses, const int32_t* values_dev,
                                const int32_t* val_offsets_dev, const uint32_t* tombstone, int64_t n,
                                uint32_t* out_mask, int num_sms, cudaStream_t stream) {

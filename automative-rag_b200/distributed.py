@@ -196,10 +196,17 @@ class ShardedCandidateMaxSim:
             lambda q, loc_cand, w: self.engine.maxsim(q, self.tokens, self.offsets, q_weight=w, cand=loc_cand))
         self._peer = local_score is None and engine is not None and self.world > 1 and engine.comm_world == self.world
 
-    def scores(self, q: torch.Tensor, cand: torch.Tensor, q_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """[nq, nc] fp32 on every rank, column j = score of cand[:, j] (-inf for padding ids)."""
+    def scores(self, q: torch.Tensor, cand: torch.Tensor, q_weight: Optional[torch.Tensor] = None, pool: int = 0
+               ) -> torch.Tensor:
+        """[nq, nc] fp32 on every rank, column j = score of cand[:, j] (-inf for padding ids).  `pool` > 0: the
+        document of a candidate is cand % pool (a corpus row id mapped onto a pool of documents)."""
         nq, nc = cand.shape
-        local = self._local_score(q, owned_candidates(cand, self.world, self.rank), q_weight)  # -inf where not owned
+        if self.engine is not None and cand.is_cuda and cand.is_contiguous() and cand.dtype in (torch.int32, torch.int64):
+            loc = self.engine.owned_candidates(cand, self.world, self.rank, pool)  # one launch
+        else:
+            c = cand if pool <= 0 else torch.where(cand >= 0, cand % pool, cand)
+            loc = owned_candidates(c, self.world, self.rank)
+        local = self._local_score(q, loc, q_weight)  # -inf where not owned
         if self.world == 1:
             return local
         if self._peer:

@@ -887,8 +887,7 @@ def extra_config5(cx):
 
     def one_query(j):
         s1, ids = index.search(queries_d[j:j + 1], k1)                      # [1, k1] global ids, same on every rank
-        slot = torch.where(ids >= 0, ids % P, torch.full_like(ids, -1)).to(torch.int32)
-        sc = rerank.scores(qtok[j:j + 1], slot)                              # [1, k1], owners' scores exchanged
+        sc = rerank.scores(qtok[j:j + 1], ids, pool=P)                       # document slot = id % P; owners' scores exchanged
         top_idx, top_sc = eng.rerank_postprocess(sc, None, k2)               # stable order, [:k2]
         return ids[0][top_idx[0].long()], top_sc[0], ids[0], s1[0], sc[0]
 
@@ -986,8 +985,7 @@ def extra_config5(cx):
     # stage-1 lists are.
     def batch_all():
         s1, ids = index.search(queries_d, k1)
-        slot = torch.where(ids >= 0, ids % P, torch.full_like(ids, -1)).to(torch.int32)
-        sc = rerank.scores(qtok, slot)
+        sc = rerank.scores(qtok, ids, pool=P)
         top_idx, top_sc = eng.rerank_postprocess(sc, None, k2)
         return torch.gather(ids, 1, top_idx.long()), top_sc, ids, s1
 

@@ -319,6 +319,16 @@ int rs_allgather(rs_handle* h, const void* local, int64_t bytes, void* out, void
  * candidate is scored by the one rank that owns its token embeddings and all others contribute
  * -inf: out[i] = max over ranks of local[i]. */
 int rs_allreduce_max_f32(rs_handle* h, const float* local, int64_t n, float* out, void* stream);
+/*
+ * Sharded MaxSim over per-query candidate lists (the reference's retrieve-then-rerank composition,
+ * tests/test_retrieval.py:206-258 with rerankers.py:351-385, run on G GPUs): documents are owned round-robin
+ * (owner = id % world, local index = id / world).  Maps n global candidate ids (int32, or int64 when cand_is_i64;
+ * negative = padding; taken modulo `pool` first when pool > 0) to this rank's local document indices, -1 for
+ * candidates another rank owns — which rs_maxsim scores -inf — so that rs_allreduce_max_f32 of the score blocks is
+ * the merged result.  One launch on `stream`.
+ */
+int rs_owned_candidates(rs_handle* h, const void* cand, int32_t cand_is_i64, int64_t n, int32_t world, int32_t rank,
+                        int64_t pool, int32_t* out_local, void* stream);
 
 /* rs_dense_topk_host against a row-sharded corpus: host queries in, merged global (score, id)
  * pairs out in host memory on every rank; H2D, local scan, the fused exchange above and the

@@ -185,3 +185,21 @@ def test_signed_zero_scores_tie(engine):
     assert i.cpu().tolist() == [[7, 20, 30, 40, 50, 1]]
     idx, out = engine.rerank_postprocess(torch.tensor([[-0.0, 0.0, -0.0, 1.0]], device=dev), None, 4)
     assert idx.cpu().tolist() == [[3, 0, 1, 2]]
+
+
+def test_owned_candidates_kernel_matches_the_host_rule(engine):
+    """rs_owned_candidates (sharded MaxSim, round-robin document ownership) against distributed.owned_candidates:
+    int32 and int64 ids, padding, every rank of worlds 1 / 2 / 8, with and without the modulo-pool mapping."""
+    from automative_rag_b200.distributed import owned_candidates
+
+    g = torch.Generator().manual_seed(5)
+    for dtype in (torch.int32, torch.int64):
+        cand = torch.randint(0, 1_000_000, (37, 211), generator=g, dtype=dtype)
+        cand[::5, ::7] = -1
+        for world in (1, 2, 8):
+            for rank in range(world):
+                for pool in (0, 12_345):
+                    got = engine.owned_candidates(cand.to(engine.device), world, rank, pool).cpu()
+                    c = cand if pool == 0 else torch.where(cand >= 0, cand % pool, cand)
+                    want = owned_candidates(c, world, rank)
+                    assert got.dtype == torch.int32 and torch.equal(got, want)
