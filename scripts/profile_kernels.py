@@ -6,6 +6,7 @@
     python scripts/profile_kernels.py maxsim_mma
     python scripts/profile_kernels.py maxsim_cand # maxsim_cand_tc5_kernel, config 4b
     python scripts/profile_kernels.py dense_batch
+    python scripts/profile_kernels.py dense_batch_c5   # 16 queries x 12.5M rows, k = 1000 (long lists)
 """
 import os
 import sys
@@ -59,6 +60,19 @@ elif what == "maxsim_cand":
     eng.set_maxsim_impl(_ffi.RS_MAXSIM_TCGEN05_CAND)
     for _ in range(iters):
         eng.maxsim(q, toks, off, cand=cand)
+elif what == "dense_batch_c5":  # config 5's stage 1 with the step's 16 queries batched: 12.5M x 1024 fp16, k1 = 1000
+    n, d, nq, k = 12_500_000, 1024, 16, 1000
+    g = torch.Generator(device=dev).manual_seed(100)
+    c = torch.empty(n, d, device=dev, dtype=torch.float16)
+    for lo in range(0, n, 500_000):
+        blk = torch.randn(min(500_000, n - lo), d, generator=g, device=dev)
+        c[lo:lo + 500_000] = (blk / blk.norm(dim=1, keepdim=True)).half()
+    q = torch.randn(nq, d, generator=g, device=dev)
+    q = (q / q.norm(dim=1, keepdim=True)).half()
+    eng.set_dense_impl(_ffi.RS_DENSE_TCGEN05)
+    for _ in range(iters):
+        eng.dense_topk(c, q, k)
+    assert eng.last_dense_redo == 0
 elif what in ("dense_batch", "dense_batch_10m"):  # dense_batch_10m = BASELINE config 3 at its full size
     n, d, nq, k = (2_000_000 if what == "dense_batch" else 10_000_000), 1024, 1024, 100
     g = torch.Generator(device=dev).manual_seed(4)
