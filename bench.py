@@ -1014,7 +1014,10 @@ def extra_config5(cx):
                              if impl_b == _ffi.RS_DENSE_TCGEN05 else "dense_scan_kernel loop",
             "queries_rerun_through_scan": redo_b,
             "roofline": {"bound": "hbm", "achieved": batch_bytes / ms_batch / 1e6, "peak": cx.hbm_peak, "unit": "GB/s per GPU",
-                         "frac": batch_bytes / ms_batch / 1e6 / cx.hbm_peak, "traffic": None, "peak_source": cx.peak_src,
+                         "frac": batch_bytes / ms_batch / 1e6 / cx.hbm_peak,
+                         "traffic": committed_traffic("dense_tc5.cu", "config5_batched_16q")
+                         if (n_local == 12_500_000 and nqs == 16 and impl_b == _ffi.RS_DENSE_TCGEN05) else None,
+                         "peak_source": cx.peak_src,
                          "note": "whole batch (one pass over the shard for all queries + exchanges + MaxSim + top-10) "
                                  "against the bytes of ONE pass over the shard"},
             "parity_vs_per_query_path": {"ok": cx.all_ok(ok_b), "identical_stage1_lists": same_lists, "identical_top10": same_top,
