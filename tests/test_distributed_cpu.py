@@ -71,6 +71,11 @@ def _worker(rank, world, port, n, d, k, nq, out_dir):
 
         sc = ShardedCandidateMaxSim(None, None, local_score=local_score).scores(queries, cand)
         np.save(os.path.join(out_dir, f"cand_{rank}.npy"), sc.numpy())
+        # config 5's mapping: the candidates are corpus row ids, the document of a row is id % pool (-1 stays padding)
+        rows = cand.long() + pool * torch.arange(nq)[:, None] * 7
+        rows[0, 0] = -1
+        sc_pool = ShardedCandidateMaxSim(None, None, local_score=local_score).scores(queries, rows, pool=pool)
+        assert torch.isneginf(sc_pool[0, 0]) and torch.equal(sc_pool.flatten()[1:], sc.flatten()[1:])
         np.save(os.path.join(out_dir, f"cand_want_{rank}.npy"),
                 (doc_score[cand.long()] + torch.arange(nq, dtype=torch.float32)[:, None]).numpy())
     finally:
