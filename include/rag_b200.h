@@ -38,7 +38,7 @@
  *       has no reference counterpart (the reference is single-GPU); it merges
  *       per-shard top-k lists after the one all-gather of SURVEY.md §8e.
  *   rs_comm_*, rs_allgather_topk, rs_allgather, rs_allreduce_max_f32,
- *   rs_dense_topk_sharded_host
+ *   rs_dense_topk_sharded_host, rs_owned_candidates
  *       the one exchange step per sharded stage (SURVEY.md §8b "rs_allgather_topk(comm, ...)",
  *       §8e) as the engine's own kernels over NVLink peer memory; no reference counterpart.
  *
